@@ -1,0 +1,308 @@
+/* bp_oracle.c - plain-C restatement of the reference BP decode path on flat CSR/CSC arrays.
+ * TEST INFRASTRUCTURE, NOT PRODUCT CODE (see bp_oracle.h). Parity status: PINNED against
+ * oracle/_ref (the unmodified reference build) by tests/test_oracle_vs_ref.py and against
+ * tests/golden/ by tests/test_oracle_golden.py.
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction: the reference is MSVC /fp:precise SSE2). */
+#include "bp_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------- .pchk I/O ---------------------------------------------------------------- */
+
+/* intio_read, intio.cpp:35-52: four bytes, low to high, two's complement; 0 on short read. */
+static int rd_i32(FILE *f, int *eof) {
+    unsigned char b[4];
+    for (int i = 0; i < 4; i++)
+        if (fread(&b[i], 1, 1, f) != 1) { *eof = 1; return 0; }
+    int top = b[3] > 127 ? (int)b[3] - 256 : b[3];
+    return (int)((unsigned)top << 24) + (b[2] << 16) + (b[1] << 8) + b[0];
+}
+/* intio_write, intio.cpp:63-80 */
+static void wr_i32(FILE *f, int v) {
+    unsigned u = (unsigned)v;
+    unsigned char b[4] = {(unsigned char)(u & 0xff), (unsigned char)((u >> 8) & 0xff),
+                          (unsigned char)((u >> 16) & 0xff), (unsigned char)((u >> 24) & 0xff)};
+    fwrite(b, 1, 4, f);
+}
+
+static int cmp_pair(const void *a, const void *b) {
+    const long long x = *(const long long *)a, y = *(const long long *)b;
+    return (x > y) - (x < y);
+}
+
+/* mod2sparse_insert (mod2sparse.cpp:502-604) keeps every row sorted by column, every column sorted by
+ * row, and merges duplicates; a sort + unique over (row,col) pairs yields the same traversal orders. */
+static orc_code *build_from_pairs(int M, int N, long long *pairs, int cnt) {
+    qsort(pairs, (size_t)cnt, sizeof(long long), cmp_pair);
+    int E = 0;
+    for (int i = 0; i < cnt; i++)
+        if (i == 0 || pairs[i] != pairs[i - 1]) pairs[E++] = pairs[i];
+    orc_code *c = (orc_code *)calloc(1, sizeof(orc_code));
+    c->M = M; c->N = N; c->E = E;
+    c->row_ptr = (int *)calloc((size_t)M + 1, sizeof(int));
+    c->col_idx = (int *)calloc((size_t)(E > 0 ? E : 1), sizeof(int));
+    c->col_ptr = (int *)calloc((size_t)N + 1, sizeof(int));
+    c->col_edge = (int *)calloc((size_t)(E > 0 ? E : 1), sizeof(int));
+    for (int e = 0; e < E; e++) {
+        int r = (int)(pairs[e] >> 32), col = (int)(pairs[e] & 0xffffffffLL);
+        c->row_ptr[r + 1]++;
+        c->col_idx[e] = col;
+        c->col_ptr[col + 1]++;
+    }
+    for (int i = 0; i < M; i++) c->row_ptr[i + 1] += c->row_ptr[i];
+    for (int j = 0; j < N; j++) c->col_ptr[j + 1] += c->col_ptr[j];
+    int *fill = (int *)calloc((size_t)N, sizeof(int));
+    for (int e = 0; e < E; e++) { /* e ascending == row ascending, so each column list is row-ascending */
+        int col = c->col_idx[e];
+        c->col_edge[c->col_ptr[col] + fill[col]++] = e;
+    }
+    free(fill);
+    return c;
+}
+
+orc_code *orc_code_from_csr(int M, int N, int E, const int *row_ptr, const int *col_idx) {
+    long long *pairs = (long long *)malloc(sizeof(long long) * (size_t)(E > 0 ? E : 1));
+    int cnt = 0;
+    for (int i = 0; i < M; i++)
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) pairs[cnt++] = ((long long)i << 32) | (unsigned)col_idx[e];
+    orc_code *c = build_from_pairs(M, N, pairs, cnt);
+    free(pairs);
+    return c;
+}
+
+/* read_pchk rcode.cpp:54-86; mod2sparse_read mod2sparse.cpp:381-427 */
+orc_code *orc_read_pchk(const char *path, int *err) {
+    int dummy; if (!err) err = &dummy;
+    *err = 0;
+    FILE *f = fopen(path, "rb");
+    if (!f) { *err = 1; return NULL; }
+    int eof = 0;
+    if (rd_i32(f, &eof) != ('P' << 8) + 0x80) { fclose(f); *err = 2; return NULL; }
+    int M = rd_i32(f, &eof);
+    if (eof || M <= 0) { fclose(f); *err = 3; return NULL; }
+    int N = rd_i32(f, &eof);
+    if (eof || N <= 0) { fclose(f); *err = 3; return NULL; }
+    int cap = 1 << 16, cnt = 0, row = -1, ok = 0;
+    long long *pairs = (long long *)malloc(sizeof(long long) * (size_t)cap);
+    for (;;) {
+        int v = rd_i32(f, &eof);
+        if (eof) break;
+        if (v == 0) { ok = 1; break; }
+        if (v < 0) { row = -v - 1; if (row >= M) break; }
+        else {
+            int col = v - 1;
+            if (col >= N) break;
+            if (row == -1) break;
+            if (cnt == cap) { cap *= 2; pairs = (long long *)realloc(pairs, sizeof(long long) * (size_t)cap); }
+            pairs[cnt++] = ((long long)row << 32) | (unsigned)col;
+        }
+    }
+    fclose(f);
+    if (!ok) { free(pairs); *err = 3; return NULL; }
+    orc_code *c = build_from_pairs(M, N, pairs, cnt);
+    free(pairs);
+    return c;
+}
+
+/* mod2sparse_write mod2sparse.cpp:338-376 (preceded by the magic word the reader expects) */
+int orc_write_pchk(const char *path, const orc_code *c) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return 0;
+    wr_i32(f, ('P' << 8) + 0x80);
+    wr_i32(f, c->M);
+    wr_i32(f, c->N);
+    for (int i = 0; i < c->M; i++) {
+        if (c->row_ptr[i] == c->row_ptr[i + 1]) continue;
+        wr_i32(f, -(i + 1));
+        for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) wr_i32(f, c->col_idx[e] + 1);
+    }
+    wr_i32(f, 0);
+    int bad = ferror(f);
+    fclose(f);
+    return !bad;
+}
+
+void orc_code_free(orc_code *c) {
+    if (!c) return;
+    free(c->row_ptr); free(c->col_idx); free(c->col_ptr); free(c->col_edge); free(c);
+}
+
+/* CheckRegular dec.cpp:138-189: D = max degree; regular flag cleared if any degree differs from the FIRST seen
+ * (note: the comparison `temp != D_v` is against the running max, which only matters for irregular codes). */
+void orc_check_regular(const orc_code *c, int *dv, int *reg_dv, int *dc, int *reg_dc) {
+    int Dv = -1, Dc = -1, rv = 1, rc = 1;
+    for (int j = 0; j < c->N; j++) {
+        int t = c->col_ptr[j + 1] - c->col_ptr[j];
+        if (Dv == -1) Dv = t; else { if (t != Dv) rv = 0; if (t > Dv) Dv = t; }
+    }
+    for (int i = 0; i < c->M; i++) {
+        int t = c->row_ptr[i + 1] - c->row_ptr[i];
+        if (Dc == -1) Dc = t; else { if (t != Dc) rc = 0; if (t > Dc) Dc = t; }
+    }
+    *dv = Dv; *reg_dv = rv; *dc = Dc; *reg_dc = rc;
+}
+
+/* ---------- syndrome ------------------------------------------------------------------ */
+
+/* check.cpp:28-47 over mod2sparse_mulvec mod2sparse.cpp:855-881 */
+int orc_check(const orc_code *c, const char *dblk, char *pchk) {
+    int w = 0;
+    for (int i = 0; i < c->M; i++) {
+        int p = 0;
+        for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) p ^= (dblk[c->col_idx[e]] & 1);
+        if (pchk) pchk[i] = (char)p;
+        w += p;
+    }
+    return w;
+}
+
+/* ---------- belief propagation, fp64 ---------------------------------------------------- */
+
+/* Iter_Belief_Propagation dec.cpp:632-694, same operations in the same order on flat arrays. */
+static void bp_iter(const orc_code *c, const double *lratio, char *dblk, double *pr, double *lr, double *post) {
+    /* check-node (row) pass, dec.cpp:644-662 */
+    for (int i = 0; i < c->M; i++) {
+        double dl = 1;
+        for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) {
+            lr[e] = dl;
+            dl *= 1 - 2 / (1 + pr[e]);
+        }
+        dl = 1;
+        for (int e = c->row_ptr[i + 1] - 1; e >= c->row_ptr[i]; e--) {
+            double t = lr[e] * dl;
+            lr[e] = (1 + t) / (1 - t);
+            dl *= 1 - 2 / (1 + pr[e]);
+        }
+    }
+    /* bit-node (column) pass, dec.cpp:667-693 */
+    for (int j = 0; j < c->N; j++) {
+        double p = lratio[j];
+        for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) {
+            int e = c->col_edge[k];
+            pr[e] = p;
+            p *= lr[e];
+        }
+        if (isnan(p)) p = 1;
+        if (post) post[j] = p;
+        dblk[j] = (p <= 1);
+        p = 1;
+        for (int k = c->col_ptr[j + 1] - 1; k >= c->col_ptr[j]; k--) {
+            int e = c->col_edge[k];
+            pr[e] *= p;
+            if (isnan(pr[e])) pr[e] = 1;
+            p *= lr[e];
+        }
+    }
+}
+
+int orc_bp_decode(const orc_code *c, const double *lratio, int max_iter, char *dblk, char *pchk,
+                  int *is_codeword, double *posterior, double *msg_pr, double *msg_lr) {
+    size_t E = (size_t)(c->E > 0 ? c->E : 1);
+    double *pr = (double *)malloc(sizeof(double) * E), *lr = (double *)malloc(sizeof(double) * E);
+    /* Init_Belief_Propagation dec.cpp:608-629 */
+    for (int e = 0; e < c->E; e++) { pr[e] = lratio[c->col_idx[e]]; lr[e] = 1; }
+    for (int j = 0; j < c->N; j++) { dblk[j] = (lratio[j] < 1); if (posterior) posterior[j] = lratio[j]; }
+    int n, w;
+    /* dec.cpp:594-599 */
+    for (n = 0;; n++) {
+        w = orc_check(c, dblk, pchk);
+        if (n == max_iter || w == 0) break;
+        bp_iter(c, lratio, dblk, pr, lr, posterior);
+    }
+    if (is_codeword) *is_codeword = (w == 0);
+    if (msg_pr) memcpy(msg_pr, pr, sizeof(double) * (size_t)c->E);
+    if (msg_lr) memcpy(msg_lr, lr, sizeof(double) * (size_t)c->E);
+    free(pr); free(lr);
+    return n;
+}
+
+long orc_bp_decode_many(const orc_code *c, const double *lratio, int F, int max_iter, char *dblk,
+                        int *iters, int *is_codeword) {
+    long tot = 0;
+    for (int f = 0; f < F; f++) {
+        int flag = 0;
+        int n = orc_bp_decode(c, lratio + (size_t)f * c->N, max_iter, dblk + (size_t)f * c->N, NULL, &flag, NULL, NULL, NULL);
+        if (iters) iters[f] = n;
+        if (is_codeword) is_codeword[f] = flag;
+        tot += n;
+    }
+    return tot;
+}
+
+/* ---------- belief propagation, fp32 (statistical parity only) --------------------------- */
+
+int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char *dblk, int *is_codeword) {
+    size_t E = (size_t)(c->E > 0 ? c->E : 1);
+    float *pr = (float *)malloc(sizeof(float) * E), *lr = (float *)malloc(sizeof(float) * E);
+    for (int e = 0; e < c->E; e++) { pr[e] = lratio[c->col_idx[e]]; lr[e] = 1; }
+    for (int j = 0; j < c->N; j++) dblk[j] = (lratio[j] < 1);
+    int n, w;
+    for (n = 0;; n++) {
+        w = orc_check(c, dblk, NULL);
+        if (n == max_iter || w == 0) break;
+        for (int i = 0; i < c->M; i++) {
+            float dl = 1;
+            for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) { lr[e] = dl; dl *= 1 - 2 / (1 + pr[e]); }
+            dl = 1;
+            for (int e = c->row_ptr[i + 1] - 1; e >= c->row_ptr[i]; e--) {
+                float t = lr[e] * dl;
+                lr[e] = (1 + t) / (1 - t);
+                dl *= 1 - 2 / (1 + pr[e]);
+            }
+        }
+        for (int j = 0; j < c->N; j++) {
+            float p = lratio[j];
+            for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) { int e = c->col_edge[k]; pr[e] = p; p *= lr[e]; }
+            if (isnan(p)) p = 1;
+            dblk[j] = (p <= 1);
+            p = 1;
+            for (int k = c->col_ptr[j + 1] - 1; k >= c->col_ptr[j]; k--) {
+                int e = c->col_edge[k];
+                pr[e] *= p;
+                if (isnan(pr[e])) pr[e] = 1;
+                p *= lr[e];
+            }
+        }
+    }
+    if (is_codeword) *is_codeword = (w == 0);
+    free(pr); free(lr);
+    return n;
+}
+
+/* ---------- likelihood setup --------------------------------------------------------------- */
+
+void orc_lr_from_llr(const double *llr, int n, double *lr) { /* DNA_main.cpp:1342-1344 */
+    for (int i = 0; i < n; i++) lr[i] = exp(llr[i]);
+}
+double orc_std_dev(double ebno_db, double rate) { /* channel.cpp:9-16 */
+    double ENL = pow(10.0, (ebno_db * 0.1));
+    double ENLxRATE = 2 * rate * ENL;
+    return 1 / sqrt(ENLxRATE);
+}
+double orc_awgn_llr(double y, double sigma) { return 2.0 * y / (sigma * sigma); } /* channel.cpp:32 */
+double orc_bsc_lr(int recv_bit, double p) { return recv_bit ? p / (1 - p) : (1 - p) / p; } /* channel.cpp:75-84 */
+double orc_vote_llr(int k, double eps) { return k * log((1 - eps) / eps); } /* decoder.py:314 */
+
+/* ---------- counter-based RNG (specification shared with the device generators) ------------ */
+
+static uint64_t mix64(uint64_t z) { /* splitmix64 finaliser */
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+uint64_t orc_rng_u64(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t stream) {
+    uint64_t x = mix64(seed * 0x9E3779B97F4A7C15ULL + frame + 0x632BE59BD9B4E019ULL);
+    x = mix64(x ^ (bit * 0xD6E8FEB86659FD93ULL + stream * 0xA0761D6478BD642FULL + 0x2545F4914F6CDD1DULL));
+    return x;
+}
+double orc_rng_uniform(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t stream) {
+    return (double)(orc_rng_u64(seed, frame, bit, stream) >> 11) * (1.0 / 9007199254740992.0);
+}
+double orc_rng_normal(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t stream) {
+    double u1 = ((double)(orc_rng_u64(seed, frame, bit, stream) >> 11) + 1.0) * (1.0 / 9007199254740992.0); /* (0,1] */
+    double u2 = orc_rng_uniform(seed, frame, bit, stream + 1);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}

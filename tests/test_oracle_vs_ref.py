@@ -1,0 +1,57 @@
+"""Pins the CPU restatement against the UNMODIFIED reference objects (oracle/_ref/libldpc_ref.so) on fresh
+seeded inputs - beyond the committed golden vectors. Skipped where oracle/_ref was never built. CPU only."""
+import numpy as np
+import pytest
+
+import oraclelib as ol
+
+pytestmark = pytest.mark.skipif(not ol.RefLib.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return ol.RefLib(ol.PCHK_18432), ol.Oracle(ol.PCHK_18432)
+
+
+def test_structure(pair):
+    ref, orc = pair
+    rp, ci = ref.export_csr()
+    assert np.array_equal(rp, orc.row_ptr) and np.array_equal(ci, orc.col_idx)
+    assert ref.check_regular() == orc.check_regular()
+
+
+def test_bitexact_random_frames(pair):
+    ref, orc = pair
+    cws = ol.load_codewords()
+    rs = np.random.RandomState(2024)
+    N = ref.N
+    for t in range(8):
+        f = int(rs.randint(272))
+        kind = t % 4
+        if kind == 0:
+            eps = [0.005, 0.0075][t // 4 % 2]
+            lr = np.where((cws[f] ^ ol.bsc_flips(100 + t, f, N, eps)) == 0, (1 - eps) / eps, eps / (1 - eps))
+        elif kind == 1:
+            sigma = 1 / np.sqrt(2 * (1 - 2048 / 18432) * 10 ** 0.42)
+            lr = np.exp(2 * (np.where(cws[f] == 0, 1.0, -1.0) + sigma * rs.randn(N)) / sigma ** 2)
+        elif kind == 2:
+            k = rs.poisson(3.7, N) - 2 * rs.binomial(4, 0.02, N)
+            lr = np.exp(np.where(cws[f] == 0, k, -k) * np.log(49.0))
+        else:
+            lr = np.exp(rs.uniform(-60, 60, N))  # garbage: exercises inf / NaN guards
+        mi = [100, 30, 100, 12][kind]
+        a = ref.decode(lr, mi, want_msgs=True)
+        b = orc.decode(lr, mi, want_msgs=True)
+        assert a["n"] == b["n"] and a["ok"] == b["ok"]
+        assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"])
+        for key in ("post", "pr", "lr"):
+            assert np.array_equal(a[key].view(np.uint64), b[key].view(np.uint64)), key
+
+
+def test_check_matches(pair):
+    ref, orc = pair
+    rs = np.random.RandomState(5)
+    d = (rs.rand(ref.N) < 0.3).astype(np.int8)
+    wa, pa = ref.check(d)
+    wb, pb = orc.check(d)
+    assert wa == wb and np.array_equal(pa, pb)
