@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py - decoded Gbit/s of the B200 BP decoder on BASELINE.json's n=18432 code (contract: see DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            the reference's own CPU implementation on the host cores
+
+A step = one pass of the hot path over one batch: F frames (default 100 000, BASELINE configs[1]) of the
+n=18432/m=2048 code, codeword[f % 272] through a BSC(eps), prprp max 100 iterations, decoded bits + iteration counts out.
+`value` = whole-job decoded Gbit/s with inputs resident in HBM; `e2e` = same through the host-buffer C-ABI call.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PCHK = os.path.join(ROOT, "tests", "golden", "decode_n18432_m2048_final.pchk")
+CW_BITS = os.path.join(ROOT, "tests", "golden", "codewords_n18432_272.bits")
+N, M, E = 18432, 2048, 147456
+B_ROW = 16 * E                 # check-node pass: read pr + write lr, 8 B each per edge
+B_COL = 16 * E + 8.25 * N      # bit-node pass: read lr + write pr, lratio, packed decisions
+B_ITER = 32 * E + 8.25 * N     # algorithmic bytes per frame-iteration (fp64)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def shard(total_frames_per_gpu, rank):
+    """Weak scaling: every rank decodes its own F frames; GLOBAL frame indices keep results independent of N."""
+    return rank * total_frames_per_gpu, total_frames_per_gpu
+
+
+def cpu_reference_run(frames_per_proc, eps, max_iter):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline
+    return cpu_baseline.run(PCHK, 0, frames_per_proc, eps, max_iter)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the same workload: `fpp` frames per host core per step
+    vals, info = [], None
+    for s in range(args.warmup + args.steps):
+        info = cpu_reference_run(args.ref_frames_per_core, args.eps, args.max_iter)
+        if s >= args.warmup:
+            vals.append(info["frames"] * N / info["decode_s"] / 1e9)
+    v = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "decoded Gbit/s, n=18432 prprp", "value": v, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["decode_s"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, info["frames"]),
+        "cpu_baseline": {"value": v, "unit": "Gbit/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": "%d frames (%d per core) x max %d iterations, eps=%g; %.2f ms per iteration per core"
+                                   % (info["frames"], args.ref_frames_per_core, args.max_iter, args.eps, info["ms_per_iter_per_core"])},
+        "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, frames):
+    return {"workload": "configs[1]: n=18432/m=2048 code (decode_n18432_m2048_final.pchk), %d-frame batch per GPU, "
+                        "codeword[f%%272] + synthetic BSC eps=%g, prprp max %d iterations" % (frames, args.eps, args.max_iter),
+            "frames_per_gpu": frames, "eps": args.eps, "max_iter": args.max_iter, "wave_frames": args.wave,
+            "l2": "inputs larger than L2: message working set %.1f GB per wave vs 126 MB L2" % (min(args.wave, frames) * E * 8 / 1e9)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    ldpc = _pkg.load()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the decoder has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    code = ldpc.Code(PCHK)
+    dec = ldpc.Decoder(code, devices=[local], wave_frames=args.wave)
+    F = args.frames
+    W = (N + 31) // 32
+    frame0, _ = shard(F, rank)
+    cw = np.fromfile(CW_BITS, dtype=np.uint8).view(np.int32).reshape(272, W)
+    d_cw = torch.from_numpy(cw).to(dev)
+    d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+    d_bits = torch.empty((F, W), dtype=torch.int32, device=dev)
+    d_it = torch.empty(F, dtype=torch.int32, device=dev)
+    d_ok = torch.empty(F, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, frame0, F, args.eps, d_in.data_ptr(), stream)
+    torch.cuda.synchronize()
+
+    def step_device():
+        dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), F, args.max_iter, param=args.eps, bits_ptr=d_bits.data_ptr(),
+                          iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=stream)
+        return dec.stats()["kernel_launches"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ev0.record()
+    for _ in range(args.steps):
+        launches += step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    frame_iters = int(d_it.sum().item())
+    t = torch.tensor([ms, float(frame_iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, frame_iters_all = float(tmax[0]), float(tsum[1])
+    else:
+        frame_iters_all = float(frame_iters)
+    value = world * F * args.steps * N / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
+    h_in = torch.empty((F, W), dtype=torch.int32).pin_memory()
+    h_in.copy_(d_in)
+    h_bits = torch.empty((F, W), dtype=torch.int32).pin_memory()
+    h_it = torch.empty(F, dtype=torch.int32).pin_memory()
+    h_ok = torch.empty(F, dtype=torch.uint8).pin_memory()
+    C = ldpc.C
+    inp = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=0, data=h_in.data_ptr(), frame_stride=0, param=args.eps, table=None)
+    out = ldpc.Output(bits=h_bits.data_ptr(), dblk=None, iters=h_it.data_ptr(), is_codeword=h_ok.data_ptr(), posterior=None, pchk=None)
+
+    def step_host():
+        rc = ldpc.lib().dnaldpc_decode_batch(dec._h, C.byref(inp), F, args.max_iter, C.byref(out))
+        if rc:
+            raise RuntimeError(ldpc.lib().dnaldpc_last_error())
+
+    e2e_steps = max(1, args.e2e_steps if args.e2e_steps > 0 else args.steps)
+    step_host()  # warm-up (staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * F * e2e_steps * N / float(te[0]) / 1e9
+    same = bool((h_it.to(dev) == d_it).all()) and bool((h_bits.to(dev) == d_bits).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: per-launch CUDA-event timing (profiling mode syncs, so it runs apart from the timed region)
+    peak, peak_src = peaks()
+    pf = min(F, args.wave)
+    dec.set_profiling(1)
+    dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), pf, min(args.max_iter, 24), param=args.eps, bits_ptr=d_bits.data_ptr(),
+                      iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    st = dec.stats()
+    dec.set_profiling(0)
+    n_it = max(1, int(d_it[:pf].max().item()))
+    act_fi = float(d_it[:pf].sum().item())  # frame-iterations actually processed by those launches
+    row_ms, col_ms = st["row_ms"] / n_it, st["col_ms"] / n_it
+    frames_per_launch = act_fi / n_it
+    if row_ms >= col_ms:
+        kname, kms, kbytes = "row_pass_kernel (check-node)", row_ms, B_ROW * frames_per_launch
+    else:
+        kname, kms, kbytes = "col_pass_kernel (bit-node)", col_ms, B_COL * frames_per_launch
+    achieved = kbytes / (kms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "launch_ms": kms, "frames_per_launch": frames_per_launch,
+            "row_ms": row_ms, "col_ms": col_ms,
+            "iteration": {"achieved": B_ITER * frames_per_launch / ((row_ms + col_ms) * 1e-3) / 1e9,
+                          "note": "B_iter=32E+8.25N per frame-iteration over row+col kernel time"},
+            "whole_step": {"achieved": B_ITER * (frame_iters_all / world) / (ms / args.steps * 1e-3) / 1e9,
+                           "note": "B_iter x frame-iterations of a step / step time (all kernels, launch gaps included)"}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("row" if row_ms >= col_ms else "col")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu:
+        info = cpu_reference_run(args.ref_frames_per_core, args.eps, args.max_iter)
+        cpu = {"value": info["frames"] * N / info["decode_s"] / 1e9, "unit": "Gbit/s", "cores": info["cores"], "kind": info["kind"],
+               "sample": "%d frames (%d per core, one pinned process per core) x max %d iterations, eps=%g; %.2f ms per iteration per core"
+                         % (info["frames"], args.ref_frames_per_core, args.max_iter, args.eps, info["ms_per_iter_per_core"])}
+
+    line = {
+        "metric": "decoded Gbit/s, n=18432 prprp", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, F),
+        "frame_iters_per_s": frame_iters_all * args.steps / (ms * 1e-3),
+        "avg_iters": frame_iters_all / (world * F),
+        "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": F * W * 4, "d2h_bytes_per_step": F * (W * 4 + 5),
+                "steps": e2e_steps, "matches_device_path": same},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=100000, help="frames per GPU per step")
+    ap.add_argument("--eps", type=float, default=0.02)
+    ap.add_argument("--max-iter", type=int, default=100)
+    ap.add_argument("--wave", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--ref-frames-per-core", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

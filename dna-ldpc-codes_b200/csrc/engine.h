@@ -1,0 +1,73 @@
+// engine.h - per-device decoder engine: owns the device copies of the H edge tables, the frame-interleaved
+// message arrays of one wave, and the host-side iteration loop (early exit on zero syndrome / max_iter,
+// dec.cpp:594-599). Internal C++ interface behind the C ABI of include/dnaldpc.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/dnaldpc.h"
+#include "../host/code.h"
+
+namespace dnaldpc {
+
+class Engine {
+  public:
+    Engine(const Code &code, int device, int precision, int wave_frames);
+    ~Engine();
+    bool ok() const { return err_.empty(); }
+    const std::string &error() const { return err_; }
+    int device() const { return device_; }
+
+    // DEVICE pointers in `in` / `out`; asynchronous on `stream` except for the lagged early-exit polls.
+    int decode_device(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out, cudaStream_t stream);
+    // HOST pointers; blocking.
+    int decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out);
+    int synth_bsc(const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0, int64_t F, double eps,
+                  uint32_t *out_bits, cudaStream_t stream);
+
+    dnaldpc_stats stats{};
+    bool profiling = false;
+
+  private:
+    template <typename T> int run_wave(const dnaldpc_input &in_dev, int nf, int max_iter, const dnaldpc_output &out_dev,
+                                       cudaStream_t st);
+    template <typename T> int launch_row(bool first, int G, cudaStream_t st);
+    template <typename T> int launch_col(int G, bool want_post, cudaStream_t st);
+    int ensure_wave(int nf, bool want_post);
+    int ensure_counters(int max_iter);
+    int fail(cudaError_t e, const char *what);
+    int fail(const std::string &m, int rc);
+    void *stage(void **buf, size_t *cap, size_t need);
+
+    std::string err_;
+    int device_ = 0, precision_ = 0, wave_frames_ = 4096;
+    int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
+    bool reg_rows_ = false, reg_cols_ = false;
+    size_t esz_ = 8;
+    // H edge tables (device)
+    int32_t *d_row_ptr_ = nullptr, *d_col_idx_ = nullptr, *d_col_ptr_ = nullptr, *d_col_edge_ = nullptr;
+    // wave state (device)
+    int cap_groups_ = 0;
+    void *d_msg_ = nullptr, *d_lratio_ = nullptr, *d_post_ = nullptr;
+    uint32_t *d_decw_ = nullptr, *d_actw_ = nullptr;
+    int32_t *d_iters_ = nullptr;
+    uint8_t *d_ok_ = nullptr;
+    double *d_table_ = nullptr;  // 256 doubles (BSC uses the first 2)
+    unsigned int *d_counters_ = nullptr, *h_counters_ = nullptr;
+    int cap_counters_ = 0;
+    static constexpr int kLag = 2;
+    cudaEvent_t ev_[kLag + 1] = {};
+    cudaEvent_t prof_ev_[3] = {};
+    cudaStream_t own_stream_ = nullptr;
+    // staging for the host-pointer path (device side)
+    void *s_in_ = nullptr, *s_bits_ = nullptr, *s_dblk_ = nullptr, *s_post_ = nullptr, *s_pchk_ = nullptr;
+    size_t c_in_ = 0, c_bits_ = 0, c_dblk_ = 0, c_post_ = 0, c_pchk_ = 0;
+    std::vector<double> h_exp_;
+};
+
+int math_selftest(long long n, uint64_t seed, long long *mismatches, std::string &err);
+
+}  // namespace dnaldpc

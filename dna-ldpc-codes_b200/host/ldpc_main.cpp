@@ -1,0 +1,266 @@
+// ldpc_main.cpp - drop-in for the reference's `ldpc` command line on its belief-propagation path.
+//
+// Grammar (SetUp, DNA_main.cpp:300-505; pipeline instance ex_decoder/def_func.py:49):
+//   ldpc <bSystematic> <decoder_type> <channel_type> <seed> <max_iter> <frame_num> [<target_frame_err> if frame_num==0]
+//        <codeword_base> <soft_base> <pchk_base> <chan_param> <punctuation> <shortening> <targeting>  [extensions]
+// Reads <codeword_base>.txt (true codeword), <soft_base>.txt (LLR = ln(p0/p1)) and <pchk_base>.pchk from the CWD,
+// writes dec_<codeword_base>.txt, result_(...).txt and the same stdout summary as the reference
+// (Set_Code :552-556, Run_Simulation :916-927, Print_One_Result :1170-1182, Print_All_Result :1048-1123).
+// Only decoder_type 0 (BP) without punctuation / shortening / targeting is in scope; anything else is rejected.
+//
+// Extensions (after the positional block, none of them changes the reference behaviour when absent):
+//   --device N        CUDA device ordinal (default 0)
+//   --fp32            optional single-precision mode (statistical parity only)
+//   --list FILE       batch mode: FILE holds one "<codeword_base> <soft_base>" pair per line; all frames are decoded
+//                     in ONE process / one batched GPU call; a dec_*.txt per frame, one result file for the batch
+//   --timing          print a JSON line with decode time and iteration counts on stderr
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "dnaldpc.h"
+#include "textio.h"
+
+using namespace dnaldpc;
+
+namespace {
+
+struct Args {
+    int bSystematic = 0, decoder_type = 0, channel_type = 0, seed = 0, max_iter = 0;
+    long frame_num = 1;
+    int target_frame_err = 0;
+    std::string cw_base, soft_base, pchk_base;
+    double chan_param = 0;
+    int punctuation = 0, shortening = 0, targeting = 0;
+    int device = 0;
+    bool fp32 = false, timing = false;
+    std::string list;
+};
+
+[[noreturn]] void die_argc() {
+    fprintf(stderr, "\n\nargc error!\n\n");  // DNA_main.cpp:494-502
+    exit(1);
+}
+
+Args parse(int argc, char **argv) {
+    Args a;
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; i++) {
+        std::string s = argv[i];
+        if (s == "--device" && i + 1 < argc) a.device = atoi(argv[++i]);
+        else if (s == "--fp32") a.fp32 = true;
+        else if (s == "--timing") a.timing = true;
+        else if (s == "--list" && i + 1 < argc) a.list = argv[++i];
+        else pos.push_back(s);
+    }
+    size_t p = 0;
+    auto next = [&]() -> const char * { if (p >= pos.size()) die_argc(); return pos[p++].c_str(); };
+    a.bSystematic = atoi(next());
+    a.decoder_type = atoi(next());
+    a.channel_type = atoi(next());
+    a.seed = atoi(next());
+    a.max_iter = atoi(next());
+    a.frame_num = atol(next());
+    if (a.frame_num == 0) a.target_frame_err = atoi(next());
+    a.cw_base = next();
+    a.soft_base = next();
+    a.pchk_base = next();
+    a.chan_param = atof(next());
+    a.punctuation = atoi(next());
+    a.shortening = atoi(next());
+    a.targeting = atoi(next());
+    if (p != pos.size()) die_argc();
+    return a;
+}
+
+void check(int rc) {
+    if (rc != DNALDPC_OK) {
+        fprintf(stderr, "%s\n", dnaldpc_last_error());
+        exit(1);
+    }
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Args a = parse(argc, argv);
+    if (a.decoder_type != 0) {
+        fprintf(stderr, "ldpc: decoder type %d is not supported by this build (only 0 = belief propagation)\n", a.decoder_type);
+        return 1;
+    }
+    if (a.punctuation || a.shortening || a.targeting) {
+        fprintf(stderr, "ldpc: punctuation / shortening / targeting are not supported by this build (pass 0 0 0)\n");
+        return 1;
+    }
+    if (a.frame_num == 0) {
+        fprintf(stderr, "ldpc: frame_num 0 (run until target frame errors) needs a channel simulator; not supported\n");
+        return 1;
+    }
+    if (a.max_iter < 0) a.max_iter = 0;
+
+    // Set_Code (DNA_main.cpp:544-609)
+    const std::string pchk_file = a.pchk_base + ".pchk";
+    dnaldpc_code *code = nullptr;
+    check(dnaldpc_code_read_pchk(pchk_file.c_str(), &code));
+    int M, N, E;
+    dnaldpc_code_dims(code, &M, &N, &E);
+    const int K = N - M;
+    printf("\ng_CODE_N : %d\ng_CODE_K : %d\ng_CODE_M : %d\n\n", N, K, M);
+    const double rate = 1.0 - (double)((double)M / (double)N);
+    const double ebno = a.channel_type == 0 ? a.chan_param : 0.0;
+    const double std_dev = dnaldpc_std_dev(ebno, rate);
+    int dv, rdv, dc, rdc;
+    dnaldpc_code_check_regular(code, &dv, &rdv, &dc, &rdc);  // LDPC_Set_Decoder -> CheckRegular
+
+    // frames: the positional pair, or every pair of --list
+    std::vector<std::pair<std::string, std::string>> frames;
+    if (a.list.empty()) frames.push_back({a.cw_base, a.soft_base});
+    else {
+        FILE *f = fopen(a.list.c_str(), "r");
+        if (!f) { fprintf(stderr, "Can't open list file: %s\n", a.list.c_str()); return 1; }
+        char c1[512], c2[512];
+        while (fscanf(f, "%511s %511s", c1, c2) == 2) frames.push_back({c1, c2});
+        fclose(f);
+        if (frames.empty()) { fprintf(stderr, "List file %s holds no \"<codeword> <soft>\" pairs\n", a.list.c_str()); return 1; }
+    }
+    const size_t F = frames.size();
+
+    time_t t_start, t_end;
+    time(&t_start);
+
+    // LDPC_Encode (DNA_main.cpp:1319-1348): codeword + LLR text, LR = exp(LLR) with the host libm
+    std::vector<signed char> codewords(F * (size_t)N);
+    std::vector<double> llr(F * (size_t)N), lr(F * (size_t)N);
+    std::string err;
+    for (size_t f = 0; f < F; f++) {
+        std::vector<signed char> cw;
+        std::vector<double> l;
+        if (!read_codeword_txt(frames[f].first + ".txt", N, cw, err) || !read_llr_txt(frames[f].second + ".txt", N, l, err)) {
+            fprintf(stderr, "%s\n", err.c_str());
+            return 1;
+        }
+        memcpy(&codewords[f * (size_t)N], cw.data(), (size_t)N);
+        memcpy(&llr[f * (size_t)N], l.data(), (size_t)N * sizeof(double));
+    }
+    for (size_t i = 0; i < lr.size(); i++) lr[i] = exp(llr[i]);
+
+    dnaldpc_config cfg{};
+    cfg.n_devices = 1;
+    cfg.devices[0] = a.device;
+    cfg.precision = a.fp32 ? DNALDPC_PREC_F32 : DNALDPC_PREC_F64;
+    cfg.wave_frames = (int)std::min<size_t>(4096, (F + 31) / 32 * 32);
+    dnaldpc_decoder *dec = nullptr;
+    check(dnaldpc_decoder_create(code, &cfg, &dec));
+
+    std::vector<unsigned char> dblk(F * (size_t)N), okflag(F);
+    std::vector<int32_t> iters(F);
+    dnaldpc_input in{};
+    in.kind = DNALDPC_IN_LR_F64;
+    in.data = lr.data();
+    dnaldpc_output out{};
+    out.dblk = dblk.data();
+    out.iters = iters.data();
+    out.is_codeword = okflag.data();
+    auto c0 = std::chrono::steady_clock::now();
+    check(dnaldpc_decode_batch(dec, &in, (int64_t)F, a.max_iter, &out));  // LDPC_Decode -> Run_Belief_Propagation_Decoder
+    auto c1 = std::chrono::steady_clock::now();
+
+    // error counting: LDPC_Raw_Error_Check (:1711-1750, sign of the LLR) and LDPC_BIT_Check (:1675-1706)
+    const int len = a.bSystematic ? K : N;
+    long long bit_err[3] = {0, 0, 0}, frame_err[3] = {0, 0, 0}, total_iter = 0;
+    for (size_t f = 0; f < F; f++) {
+        long long raw = 0, dec_err = 0;
+        for (int i = 0; i < len; i++) {
+            const int hard = llr[f * (size_t)N + i] >= 0 ? 0 : 1;
+            raw += (codewords[f * (size_t)N + i] != hard);
+            dec_err += (codewords[f * (size_t)N + i] != (signed char)dblk[f * (size_t)N + i]);
+        }
+        bit_err[0] += raw; frame_err[0] += raw > 0;
+        bit_err[1] += dec_err; frame_err[1] += dec_err > 0;
+        bit_err[2] += dec_err; frame_err[2] += dec_err > 0;
+        total_iter += iters[f];
+    }
+    // frame_num > 1 re-reads the same files and repeats the identical decode (DNA_main.cpp:1319-1348): counters scale
+    const long long reps = a.list.empty() ? a.frame_num : 1;
+    const long long n_frames = (long long)F * reps;
+    for (int i = 0; i < 3; i++) { bit_err[i] *= reps; frame_err[i] *= reps; }
+
+    // dec_<codeword_base>.txt (:916-927); the file name is printed without a newline (:918)
+    for (size_t f = 0; f < F; f++) {
+        const std::string dec_name = "dec_" + frames[f].first + ".txt";
+        if (!write_dec_txt(dec_name, &dblk[f * (size_t)N], N, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        if (f + 1 == F) printf("%s", dec_name.c_str());
+    }
+    time(&t_end);
+
+    // Print_One_Result (:1170-1182)
+    printf("\n");
+    if (a.channel_type == 2) printf("[%d]  code : (%d,%d)\trate : %.3f\tEps : %.2f \n", 0, N, K, rate, a.chan_param);
+    else printf("[%d]  code : (%d,%d)\trate : %.3f\tEb/No : %.2f dB\n", 0, N, K, rate, ebno);
+    printf("[%d]  frame_num              : %lld\n", 0, n_frames);
+    printf("[%d]  bit_err                : %lld\n", 0, bit_err[2]);
+    printf("[%d]  frame_err              : %lld\n", 0, frame_err[2]);
+    printf("[%d]  without coding (bit)   : %lld\n", 0, bit_err[0]);
+    printf("[%d]  without coding (frame) : %lld\n\n", 0, frame_err[0]);
+
+    // Print_All_Result (:965-1123)
+    char name[1024];
+    const std::string soft_file = (a.list.empty() ? a.soft_base : a.list) + (a.list.empty() ? ".txt" : "");
+    if (a.channel_type == 2)
+        snprintf(name, sizeof(name), "result_(%s)_%s_%d_%.3f_%d_%d_%d.txt", soft_file.c_str(), pchk_file.c_str(), a.decoder_type, a.chan_param, 0, a.max_iter, a.seed);
+    else if (a.channel_type == 1)
+        snprintf(name, sizeof(name), "result_(%s)_%s_%d_%.4f_%d_%d_%d.txt", soft_file.c_str(), pchk_file.c_str(), a.decoder_type, a.chan_param, 0, a.max_iter, a.seed);
+    else
+        snprintf(name, sizeof(name), "result_(%s)_%s_%d_%.3fdB_%d_%d_%d.txt", soft_file.c_str(), pchk_file.c_str(), a.decoder_type, ebno, 0, a.max_iter, a.seed);
+    FILE *fp = fopen(name, "w");
+    if (!fp) { fprintf(stderr, "Can't create %s\n", name); return 1; }
+    fprintf(fp, "code N        : %d\n", N);
+    fprintf(fp, "code K        : %d\n", K);
+    fprintf(fp, "code M        : %d\n", M);
+    fprintf(fp, "code rate     : %.3f\n", rate);
+    if (a.channel_type == 2) fprintf(fp, "Eps\t\t: %.3f \n", a.chan_param);
+    else {
+        fprintf(fp, "Eb/No         : %.2f dB\n", ebno);
+        fprintf(fp, "g_std_dev     : %.2f\n", std_dev);
+    }
+    fprintf(fp, "max iteration : %d\n", a.max_iter);
+    fprintf(fp, "dv            : %d\n", dv);
+    fprintf(fp, "bRegular_dv   : %d\n", rdv);
+    fprintf(fp, "dc            : %d\n", dc);
+    fprintf(fp, "bRegular_dc   : %d\n", rdc);
+    fprintf(fp, "=============================================\n");
+    fprintf(fp, "                 result\n");
+    fprintf(fp, "=============================================\n");
+    double d = difftime(t_end, t_start);
+    const int tm_hour = (int)(d / 3600); d -= tm_hour * 3600;
+    const int tm_min = (int)(d / 60); d -= tm_min * 60;
+    const int tm_sec = (int)d;
+    fprintf(fp, "start time      : %s", ctime(&t_start));
+    fprintf(fp, "end time        : %s", ctime(&t_end));
+    fprintf(fp, "simulation time : %d hours %d mins %d secs\n\n", tm_hour, tm_min, tm_sec);
+    fprintf(fp, "# of processes         : %d\n", 1);
+    fprintf(fp, "initial seed value     : %d\n\n", a.seed);
+    for (int i = 0; i < 2; i++) fprintf(fp, "# of Frame[%2d]          :%lld\n", i, n_frames);
+    fprintf(fp, "\n");
+    for (int i = 0; i < 2; i++) fprintf(fp, "# of Bit Errors[%2d]     : %lld\n", i, bit_err[i]);
+    fprintf(fp, "\n");
+    const double denom = (double)len * (double)n_frames;
+    for (int i = 0; i < 2; i++) fprintf(fp, "BER[%2d]                 : %.5e\n", i, (double)bit_err[i] / denom);
+    fprintf(fp, "\n");
+    fclose(fp);
+
+    if (a.timing) {
+        const double ms = std::chrono::duration<double, std::milli>(c1 - c0).count();
+        fprintf(stderr, "{\"frames\": %zu, \"decode_ms\": %.3f, \"total_iterations\": %lld, \"converged\": %lld}\n", F, ms,
+                total_iter, (long long)F - frame_err[2] / (reps ? reps : 1));
+    }
+    dnaldpc_decoder_destroy(dec);
+    dnaldpc_code_free(code);
+    return 0;
+}

@@ -1,0 +1,93 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/dnaldpc.h declares, the host
+logic (.pchk reader/writer, CSR/CSC tables, CheckRegular, channel tables) matches the oracle, and creating a decoder
+without a GPU fails loudly (no CPU fallback). No compute calls here."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import _pkg
+import gen_regular_pchk
+import oraclelib as ol
+
+ldpc = _pkg.load()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "dnaldpc.h")).read()
+    declared = set(re.findall(r"\b(dnaldpc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(ldpc.EXPORTS), declared ^ set(ldpc.EXPORTS)
+    L = C.CDLL(ldpc.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in ldpc.lib().dnaldpc_version()
+
+
+def test_pchk_reader_matches_oracle(tmp_path):
+    code = ldpc.Code(ol.PCHK_18432)
+    orc = ol.Oracle(ol.PCHK_18432)
+    assert (code.M, code.N, code.E) == (2048, 18432, 147456)
+    rp, ci, cp, ce = code.export()
+    assert np.array_equal(rp, orc.row_ptr) and np.array_equal(ci, orc.col_idx)
+    assert np.array_equal(cp, orc.col_ptr) and np.array_equal(ce, orc.col_edge)
+    assert code.check_regular() == orc.check_regular() == (8, 1, 72, 1)
+    out = str(tmp_path / "rt.pchk")
+    code.write_pchk(out)
+    assert open(out, "rb").read() == open(ol.PCHK_18432, "rb").read()
+
+
+def test_pchk_irregular_and_errors(tmp_path):
+    p = str(tmp_path / "x.pchk")
+    # unsorted rows + duplicate entry: merged and sorted like mod2sparse_insert
+    open(p, "wb").write(struct.pack("<12i", 0x5080, 2, 4, -2, 4, 1, 1, -1, 3, 2, 3, 0))
+    c = ldpc.Code(p)
+    o = ol.Oracle(p)
+    rp, ci, cp, ce = c.export()
+    assert c.E == 4 and list(rp) == [0, 2, 4] and list(ci) == [1, 2, 0, 3]
+    assert np.array_equal(cp, o.col_ptr) and np.array_equal(ce, o.col_edge)
+    assert c.check_regular() == o.check_regular()
+    for words, rc in [((0x5081, 2, 4, 0), 3), ((0x5080, 2, 4, -1, 5, 0), 3), ((0x5080, 2, 4, 1, 0), 3),
+                      ((0x5080, 2, 4, -1, 1), 3), ((0x5080, 0, 4, 0), 3), ((0x5080, 2, 4, -3, 1, 0), 3)]:
+        open(p, "wb").write(struct.pack("<%di" % len(words), *words))
+        with pytest.raises(ldpc.LdpcError) as ei:
+            ldpc.Code(p)
+        assert ei.value.rc == rc
+    with pytest.raises(ldpc.LdpcError) as ei:
+        ldpc.Code(str(tmp_path / "missing.pchk"))
+    assert ei.value.rc == 2 and "Can't open parity check file" in str(ei.value)
+
+
+def test_from_csr_and_generated_code():
+    row_ptr, col_idx = gen_regular_pchk.gen_regular(120, 60, 3, 1)
+    c = ldpc.Code(csr=(60, 120, row_ptr, col_idx))
+    o = ol.Oracle(csr=(60, 120, row_ptr, col_idx))
+    rp, ci, cp, ce = c.export()
+    assert np.array_equal(rp, o.row_ptr) and np.array_equal(ci, o.col_idx) and np.array_equal(ce, o.col_edge)
+    with pytest.raises(ldpc.LdpcError):
+        ldpc.Code(csr=(60, 120, row_ptr, col_idx + 1000))
+
+
+def test_channel_helpers_match_oracle():
+    L = ol.Oracle.lib()
+    assert ldpc.std_dev(4.3, 1 - 2048 / 18432) == L.orc_std_dev(4.3, 1 - 2048 / 18432)
+    t = ldpc.bsc_table(0.02)
+    assert t[0] == L.orc_bsc_lr(0, 0.02) and t[1] == L.orc_bsc_lr(1, 0.02)
+    v = ldpc.vote_table(0.02)
+    llr = np.array([L.orc_vote_llr(k, 0.02) for k in range(-128, 128)])
+    lr = np.zeros(256)
+    L.orc_lr_from_llr(llr, 256, lr)
+    assert np.array_equal(v, lr)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    code = ldpc.Code(ol.PCHK_18432)
+    with pytest.raises(ldpc.LdpcError) as ei:
+        ldpc.Decoder(code)
+    assert ei.value.rc == 4 and "no CPU fallback" in str(ei.value)

@@ -1,0 +1,79 @@
+"""The `ldpc` command line against outputs of the UNMODIFIED reference CLI (oracle/_ref/ldpc_ref, captured by
+tools/make_golden.py): same argv (the pipeline's call, ex_decoder/def_func.py:49), same files in, byte-identical
+stdout / dec_*.txt and identical result_*.txt apart from the two wall-clock lines."""
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oraclelib as ol
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LDPC = os.path.join(ROOT, "dna-ldpc-codes_b200", "ldpc")
+
+
+def _write_inputs(tmp, f, llr, cws):
+    cwname, softname = "codeword_n18432_m1860_%d" % (f + 1), "soft_test_%d" % (f + 1)
+    with open(os.path.join(tmp, cwname + ".txt"), "w") as fh:
+        fh.write("".join("%d " % b for b in cws[f]))
+    with open(os.path.join(tmp, softname + ".txt"), "w") as fh:
+        fh.write("\n".join(str(float(x)) for x in llr))  # def_func.py:54-57 writes str(float)
+    return cwname, softname
+
+
+def _strip_times(txt):
+    return [l for l in txt.splitlines() if not l.startswith(("start time", "end time", "simulation time"))]
+
+
+@pytest.mark.parametrize("tag,f", [("a", 0), ("b", 1)])
+def test_cli_matches_reference(tmp_path, tag, f):
+    tmp = str(tmp_path)
+    cws = ol.load_codewords()
+    shutil.copyfile(ol.PCHK_18432, os.path.join(tmp, "decode_n18432_m2048_final.pchk"))
+    llr = np.load(os.path.join(ol.GOLDEN, "cli_case_%s_llr.npy" % tag))
+    cwname, softname = _write_inputs(tmp, f, llr, cws)
+    res = subprocess.run([LDPC, "0", "0", "0", "7", "200", "1", cwname, softname, "decode_n18432_m2048_final", "0", "0", "0", "0"],
+                         cwd=tmp, capture_output=True)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout == open(os.path.join(ol.GOLDEN, "cli_case_%s_stdout.txt" % tag), "rb").read()
+    dec = open(os.path.join(tmp, "dec_%s.txt" % cwname), "rb").read()
+    assert hashlib.sha256(dec).hexdigest() == open(os.path.join(ol.GOLDEN, "cli_case_%s_dec.sha256" % tag)).read().strip()
+    resname = "result_(%s.txt)_decode_n18432_m2048_final.pchk_0_0.000dB_0_200_7.txt" % softname
+    got = open(os.path.join(tmp, resname)).read()
+    want = open(os.path.join(ol.GOLDEN, "cli_case_%s_result.txt" % tag)).read()
+    assert _strip_times(got) == _strip_times(want)
+
+
+def test_cli_errors_and_batch_list(tmp_path):
+    tmp = str(tmp_path)
+    cws = ol.load_codewords()
+    # argc mismatch -> "argc error!" + exit 1 (DNA_main.cpp:494-502); unreadable pchk -> exit 1 (rcode.cpp:60-64)
+    r = subprocess.run([LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "c", "0", "0", "0"], cwd=tmp, capture_output=True)
+    assert r.returncode == 1 and b"argc error!" in r.stderr
+    r = subprocess.run([LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "nope", "0", "0", "0", "0"], cwd=tmp, capture_output=True)
+    assert r.returncode == 1 and b"Can't open parity check file: nope.pchk" in r.stderr
+    shutil.copyfile(ol.PCHK_18432, os.path.join(tmp, "H.pchk"))
+    r = subprocess.run([LDPC, "0", "3", "0", "7", "200", "1", "a", "b", "H", "0", "0", "0", "0"], cwd=tmp, capture_output=True)
+    assert r.returncode == 1 and b"not supported" in r.stderr
+    r = subprocess.run([LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "H", "0", "0", "0", "0"], cwd=tmp, capture_output=True)
+    assert r.returncode == 1 and b"Can't open input file: a.txt" in r.stderr
+    # --list: 5 frames in one process; every dec file equals the single-frame run's
+    names = []
+    for f in range(5):
+        eps = 0.006
+        llr = np.where((cws[f] ^ ol.bsc_flips(7, f, 18432, eps)) == 0, 1.0, -1.0) * np.log((1 - eps) / eps)
+        names.append(_write_inputs(tmp, f, llr, cws))
+    with open(os.path.join(tmp, "frames.lst"), "w") as fh:
+        fh.write("".join("%s %s\n" % n for n in names))
+    r = subprocess.run([LDPC, "0", "0", "0", "7", "200", "1", "x", "x", "H", "0", "0", "0", "0", "--list", "frames.lst", "--timing"],
+                       cwd=tmp, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert b'"frames": 5' in r.stderr
+    for f, (cwname, _) in enumerate(names):
+        got = np.array(open(os.path.join(tmp, "dec_%s.txt" % cwname)).read().split(), dtype=np.int8)
+        assert np.array_equal(got, cws[f])
+    assert b"frame_num              : 5" in r.stdout and b"bit_err                : 0" in r.stdout

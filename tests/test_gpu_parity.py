@@ -1,0 +1,270 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every decode goes through the C ABI (libdnaldpc.so via
+ctypes) and is compared with (a) the golden vectors produced by the unmodified reference and (b) the CPU oracle
+(oracle/liboracle.so) on the same seeded inputs. fp64 bar: decoded bits, iteration counts, success flags, syndromes
+AND posteriors bit-exact (tolerance 0; north_star allows 1e-9 relative on posteriors)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import _pkg
+import gen_regular_pchk
+import oraclelib as ol
+
+pytestmark = pytest.mark.gpu
+ldpc = _pkg.load()
+
+
+@pytest.fixture(scope="module")
+def code18432():
+    return ldpc.Code(ol.PCHK_18432)
+
+
+@pytest.fixture(scope="module")
+def dec18432(code18432):
+    d = ldpc.Decoder(code18432, wave_frames=256)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def orc18432():
+    return ol.Oracle(ol.PCHK_18432)
+
+
+@pytest.fixture(scope="module")
+def cws():
+    return ol.load_codewords()
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def _golden_check(dec, g, N):
+    names = [str(n) for n in g["names"]]
+    by_iter = {}
+    for n in names:
+        by_iter.setdefault(int(g[n + ".max_iter"]), []).append(n)
+    for mi, group in by_iter.items():  # one batch per max_iter: frames of very different lengths share a warp group
+        lr = np.stack([g[n + ".lratio"] for n in group])
+        r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=("bits", "dblk", "iters", "ok", "post", "pchk"))
+        for k, n in enumerate(group):
+            assert r["iters"][k] == int(g[n + ".n"]), n
+            assert r["ok"][k] == int(g[n + ".ok"]), n
+            assert np.array_equal(np.packbits(r["bits"][k].astype(np.uint8), bitorder="little"), g[n + ".dblk"]), n
+            assert np.array_equal(r["dblk"][k], r["bits"][k]), n
+            assert np.array_equal(np.packbits(r["pchk"][k], bitorder="little"), g[n + ".pchk"]), n
+            assert np.array_equal(_sha(r["post"][k]), g[n + ".post_sha"]), n
+            if n + ".post" in g:
+                assert np.array_equal(r["post"][k].view(np.uint64), g[n + ".post"].view(np.uint64)), n
+
+
+def test_math_sequences_match_ieee_division():
+    """The inlined MUFU.RCP64H + Newton sequences equal nvcc's full-range IEEE division on 2^26 operands."""
+    assert ldpc.selftest_math(1 << 26, seed=12345) == 0
+
+
+def test_golden_n18432(dec18432):
+    _golden_check(dec18432, np.load(os.path.join(ol.GOLDEN, "golden_n18432.npz")), 18432)
+
+
+def test_golden_small():
+    code = ldpc.Code(os.path.join(ol.GOLDEN, "small_n120_m60.pchk"))
+    dec = ldpc.Decoder(code)
+    _golden_check(dec, np.load(os.path.join(ol.GOLDEN, "golden_small.npz")), 120)
+    dec.close()
+
+
+def test_golden_n65536(tmp_path):
+    g = np.load(os.path.join(ol.GOLDEN, "golden_n65536.npz"))
+    row_ptr, col_idx = gen_regular_pchk.gen_regular(65536, 6554, 3, 5)
+    path = str(tmp_path / "big.pchk")
+    gen_regular_pchk.write_pchk(path, 6554, 65536, row_ptr, col_idx)
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == str(g["pchk_sha256"])
+    dec = ldpc.Decoder(ldpc.Code(path))
+    _golden_check(dec, g, 65536)
+    dec.close()
+
+
+def _bsc_lr(cw, flips, p):
+    return np.where((cw ^ flips) == 0, (1 - p) / p, p / (1 - p)).astype(np.float64)
+
+
+def test_batch_vs_oracle_mixed_convergence(code18432, orc18432, cws):
+    """70 frames (ragged last group, 3 waves of 32) whose iteration counts differ inside one warp group."""
+    N = 18432
+    F = 70
+    eps_list = [0.004, 0.006, 0.0075, 0.0085, 0.02]
+    lr = np.zeros((F, N))
+    for f in range(F):
+        eps = eps_list[f % len(eps_list)]
+        lr[f] = _bsc_lr(cws[f % 272], ol.bsc_flips(21, f, N, eps), eps)
+    lr[5] = _bsc_lr(cws[5], np.zeros(N, np.int8), 0.02)  # noiseless: n == 0
+    want = ("bits", "iters", "ok", "post", "pchk")
+    for wave in (32, 64, 4096):
+        dec = ldpc.Decoder(code18432, wave_frames=wave)
+        r = dec.decode(ldpc.IN_LR_F64, lr, 30, want=want)
+        dec.close()
+        for f in range(F):
+            o = orc18432.decode(lr[f], 30)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (wave, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]), (wave, f)
+            assert np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (wave, f)
+            assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, f)
+        assert r["iters"][5] == 0 and r["ok"][5] == 1
+    assert len(set(r["iters"][:32].tolist())) > 3  # the mask logic really was exercised
+
+
+def test_input_kinds(dec18432, orc18432, cws):
+    N = 18432
+    rs = np.random.RandomState(77)
+    F = 12
+    # BSC packed bits == LR_F64 with the two-entry table
+    p = 0.006
+    recv = np.stack([cws[f] ^ ol.bsc_flips(5, f, N, p) for f in range(F)]).astype(np.uint8)
+    packed = np.packbits(recv, axis=1, bitorder="little").view(np.uint32)
+    a = dec18432.decode(ldpc.IN_BSC_BITS, packed, 50, param=p, want=("bits", "iters", "ok", "post"))
+    t = ldpc.bsc_table(p)
+    b = dec18432.decode(ldpc.IN_LR_F64, t[recv], 50, want=("bits", "iters", "ok", "post"))
+    for k in ("bits", "iters", "ok"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["post"].view(np.uint64), b["post"].view(np.uint64))
+    o = orc18432.decode(t[recv[3]], 50)
+    assert a["iters"][3] == o["n"] and np.array_equal(a["bits"][3], o["dblk"])
+    # vote counts (decoder.py:292-316): int8 k, LR = table[k+128]
+    reads = rs.poisson(3.9, (F, N))
+    wrong = rs.binomial(reads, 0.01)
+    k = (reads - 2 * wrong)
+    k = np.where(cws[:F] == 0, k, -k).astype(np.int8)
+    vt = ldpc.vote_table(0.02)
+    a = dec18432.decode(ldpc.IN_VOTE_I8, k, 100, param=0.02, want=("bits", "iters", "ok", "post"))
+    for f in range(0, F, 5):
+        o = orc18432.decode(vt[k[f].astype(np.int64) + 128], 100)
+        assert a["iters"][f] == o["n"] and a["ok"][f] == o["ok"] and np.array_equal(a["bits"][f], o["dblk"])
+        assert np.array_equal(a["post"][f].view(np.uint64), o["post"].view(np.uint64))
+    assert a["ok"].all() and np.array_equal(a["bits"], cws[:F])
+    # user-supplied table
+    a2 = dec18432.decode(ldpc.IN_VOTE_I8, k, 100, table=vt, want=("bits", "iters"))
+    assert np.array_equal(a2["bits"], a["bits"]) and np.array_equal(a2["iters"], a["iters"])
+    # LLR with host exp == the reference's LDPC_Encode (exp by libm); device exp agrees to the last ulp or two
+    llr = np.where(recv == 0, 1.0, -1.0) * np.log((1 - p) / p) * rs.uniform(0.6, 1.4, (F, N))
+    lr = np.zeros_like(llr)
+    ol.Oracle.lib().orc_lr_from_llr(llr.reshape(-1), llr.size, lr.reshape(-1))
+    a = dec18432.decode(ldpc.IN_LLR_F64, llr, 50, flags=ldpc.FLAG_HOST_EXP, want=("bits", "iters", "ok", "post"))
+    for f in (0, 7):
+        o = orc18432.decode(lr[f], 50)
+        assert a["iters"][f] == o["n"] and np.array_equal(a["bits"][f], o["dblk"])
+        assert np.array_equal(a["post"][f].view(np.uint64), o["post"].view(np.uint64))
+    d = dec18432.decode(ldpc.IN_LLR_F64, llr, 50, want=("bits", "iters", "ok", "post"))
+    assert np.array_equal(d["ok"], a["ok"]) and np.array_equal(d["bits"][a["ok"] == 1], a["bits"][a["ok"] == 1])
+    # AWGN: LLR = 2y/sigma^2 (channel.cpp:32); exp on the device, so compare at the decision level
+    sigma = ldpc.std_dev(4.6, 1 - 2048 / 18432)
+    y = np.where(cws[:F] == 0, 1.0, -1.0) + sigma * rs.randn(F, N)
+    a64 = dec18432.decode(ldpc.IN_AWGN_F64, y, 100, param=sigma, want=("bits", "iters", "ok"))
+    ref_lr = np.exp(2.0 * y / (sigma * sigma))
+    n_ref = np.array([orc18432.decode(ref_lr[f], 100)["n"] for f in range(F)])
+    assert a64["ok"].all() and np.array_equal(a64["bits"], cws[:F])
+    assert np.mean(a64["iters"] == n_ref) >= 0.9
+    a32 = dec18432.decode(ldpc.IN_AWGN_F32, y.astype(np.float32), 100, param=sigma, want=("bits", "ok"))
+    assert a32["ok"].all() and np.array_equal(a32["bits"], cws[:F])
+
+
+def test_run_bp_decoder_dropin(dec18432, orc18432, cws):
+    """Same buffer contract as Run_Belief_Propagation_Decoder(H, lratio, dblk, pchk, &bIsCodeword) -> n."""
+    N = 18432
+    for eps, mi in [(0.006, 200), (0.02, 7)]:
+        lr = _bsc_lr(cws[9], ol.bsc_flips(7, 9, N, eps), eps)
+        r = dec18432.run_bp_decoder(lr, mi)
+        o = orc18432.decode(lr, mi)
+        assert r["n"] == o["n"] and r["ok"] == o["ok"]
+        assert np.array_equal(r["dblk"], o["dblk"]) and np.array_equal(r["pchk"], o["pchk"])
+
+
+def test_edge_cases(dec18432, cws):
+    N = 18432
+    # empty batch
+    r = dec18432.decode(ldpc.IN_LR_F64, np.zeros((0, N)), 10)
+    assert r["iters"].shape == (0,)
+    # max_iter == 0: decision is the channel hard decision, success only for codewords
+    lr = np.stack([_bsc_lr(cws[0], np.zeros(N, np.int8), 0.02), _bsc_lr(cws[1], ol.bsc_flips(1, 1, N, 0.01), 0.01)])
+    r = dec18432.decode(ldpc.IN_LR_F64, lr, 0)
+    assert list(r["iters"]) == [0, 0] and list(r["ok"]) == [1, 0]
+    assert np.array_equal(r["bits"], (lr < 1).astype(np.int8))
+    # all-erased frame (LR == 1 everywhere): ties -> 0 at init (lratio < 1), zero syndrome, n == 0
+    r = dec18432.decode(ldpc.IN_LR_F64, np.ones((1, N)), 5)
+    assert r["iters"][0] == 0 and r["ok"][0] == 1 and not r["bits"].any()
+    # invalid likelihood ratios (negative / NaN) take the IEEE slow path instead of corrupting neighbours
+    lr = np.stack([_bsc_lr(cws[2], ol.bsc_flips(2, 2, N, 0.006), 0.006)] * 2)
+    lr[1, 100] = -3.0
+    lr[1, 200] = np.nan
+    r = dec18432.decode(ldpc.IN_LR_F64, lr, 20)
+    assert r["ok"][0] == 1 and np.array_equal(r["bits"][0], cws[2])
+    # argument errors
+    with pytest.raises(ldpc.LdpcError):
+        dec18432.decode(ldpc.IN_BSC_BITS, np.zeros((1, 576), np.uint32), 5, param=0.0)
+    with pytest.raises(ldpc.LdpcError):
+        dec18432.decode(ldpc.IN_LR_F64, np.ones((1, N)), -1)
+
+
+def test_invalid_inputs_match_oracle(dec18432, orc18432, cws):
+    """Negative ratios are outside the model, but the arithmetic is still IEEE: the slow path must agree."""
+    N = 18432
+    lr = _bsc_lr(cws[3], ol.bsc_flips(3, 3, N, 0.006), 0.006)
+    lr[::501] = -lr[::501]
+    r = dec18432.decode(ldpc.IN_LR_F64, lr[None], 6, want=("bits", "iters", "ok"))
+    o = orc18432.decode(lr, 6)
+    assert r["iters"][0] == o["n"] and r["ok"][0] == o["ok"] and np.array_equal(r["bits"][0], o["dblk"])
+
+
+def test_synth_generator_and_roundtrip(code18432, cws):
+    """Device generator == numpy twin of the counter RNG; encode -> BSC -> decode returns the codewords (size-
+    independent property used at full batch sizes), and results do not depend on the wave size."""
+    import torch
+    N, W = 18432, 576
+    dec = ldpc.Decoder(code18432, wave_frames=1024)
+    F = 2048 + 17
+    cw_packed = np.packbits(cws.astype(np.uint8), axis=1, bitorder="little").view(np.uint32)
+    d_cw = torch.from_numpy(cw_packed.astype(np.int32)).cuda()
+    d_in = torch.empty((F, W), dtype=torch.int32, device="cuda")
+    eps = 0.004
+    dec.synth_bsc_device(d_cw.data_ptr(), 272, 99, 1000, F, eps, d_in.data_ptr())
+    torch.cuda.synchronize()
+    got = d_in.cpu().numpy().view(np.uint32)
+    for f in (0, 271, 272, F - 1):
+        recv = cws[(1000 + f) % 272] ^ ol.bsc_flips(99, 1000 + f, N, eps)
+        assert np.array_equal(np.packbits(recv.astype(np.uint8), bitorder="little").view(np.uint32), got[f])
+    d_bits = torch.empty((F, W), dtype=torch.int32, device="cuda")
+    d_it = torch.empty(F, dtype=torch.int32, device="cuda")
+    d_ok = torch.empty(F, dtype=torch.uint8, device="cuda")
+    dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), F, 100, param=eps, bits_ptr=d_bits.data_ptr(),
+                      iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool(d_ok.all())
+    want = cw_packed[(1000 + np.arange(F)) % 272]
+    assert np.array_equal(d_bits.cpu().numpy().view(np.uint32), want)
+    it = d_it.cpu().numpy()
+    assert it.min() >= 1 and it.max() < 30
+    # a different wave size gives identical iteration counts
+    dec2 = ldpc.Decoder(code18432, wave_frames=96)
+    r = dec2.decode(ldpc.IN_BSC_BITS, got[:200], 100, param=eps)
+    assert np.array_equal(r["iters"], it[:200])
+    dec.close(); dec2.close()
+
+
+def test_multi_device_sharding(code18432, cws):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    N = 18432
+    F = 100
+    lr = np.stack([_bsc_lr(cws[f], ol.bsc_flips(4, f, N, 0.006), 0.006) for f in range(F)])
+    one = ldpc.Decoder(code18432, devices=[0])
+    two = ldpc.Decoder(code18432, devices=[0, 1])
+    a = one.decode(ldpc.IN_LR_F64, lr, 50, want=("bits", "iters", "ok", "post"))
+    b = two.decode(ldpc.IN_LR_F64, lr, 50, want=("bits", "iters", "ok", "post"))
+    for k in ("bits", "iters", "ok"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(a["post"].view(np.uint64), b["post"].view(np.uint64))
+    one.close(); two.close()
