@@ -190,7 +190,8 @@ class Decoder:
             res["pchk"] = np.zeros((F, M), np.uint8); out.pchk = res["pchk"].ctypes.data
         _check(lib().dnaldpc_decode_batch(self._h, C.byref(inp), F, max_iter, C.byref(out)))
         if "bits" in want:
-            res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, -1), axis=1, bitorder="little")[:, :N].astype(np.int8)
+            res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
+                                        bitorder="little")[:, :N].astype(np.int8)
         return res
 
     def run_bp_decoder(self, lratio, max_iter):
