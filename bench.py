@@ -87,6 +87,19 @@ def shard(total_frames_per_gpu, rank):
     return rank * total_frames_per_gpu, total_frames_per_gpu
 
 
+def aggregate(ms, frame_iters, device, world):
+    """Whole-job figures from per-rank ones: time = MAX over ranks (device time), work = SUM over ranks.
+    The only cross-rank traffic of the whole job (two doubles); the data path has no collective."""
+    if world <= 1:
+        return float(ms), float(frame_iters)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(ms), float(frame_iters)], dtype=torch.float64, device=device)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    return float(tmax[0]), float(tsum[1])
+
+
 def cpu_reference_run(frames_per_proc, eps, max_iter):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline
@@ -181,13 +194,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     frame_iters = int(d_it.sum().item())
-    t = torch.tensor([ms, float(frame_iters)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, frame_iters_all = float(tmax[0]), float(tsum[1])
-    else:
-        frame_iters_all = float(frame_iters)
+    ms, frame_iters_all = aggregate(ms, frame_iters, dev, world)
     value = world * F * args.steps * N / (ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)

@@ -33,8 +33,6 @@ template <typename T> __device__ __forceinline__ void st_stream(T *p, T v) { __s
 // FIRST: iteration 0 of a frame reads pr_e = lratio[col(e)] (Init_Belief_Propagation, dec.cpp:608-629) instead of msg,
 // which removes the E-sized initialisation write.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRowWarps = 4;
-
 // Out-of-line fallback for one (check, frame) whose inputs left the proven operand ranges. Same operations in the
 // same order as the reference, with nvcc's full-range divisions; F_k is re-derived for every k (O(deg^2)) because the
 // single in-place message array has no room to park it. Reached only with invalid (negative / NaN) likelihood ratios.
@@ -51,29 +49,9 @@ __device__ __noinline__ void row_slow_path(T *base, const T *lr_lane, const int3
     }
 }
 
+// The arithmetic of one (check, frame): d[] holds pr_k on entry; writes lr_k to base[k*32]. One basic block.
 template <typename T, int DC, bool EXACT, bool FIRST>
-__global__ void __launch_bounds__(kRowWarps * 32)
-row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int M, int N, int E, int G) {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (item >= (long long)G * M) return;
-    const int g = (int)(item / M), i = (int)(item - (long long)g * M);
-    if (!((actw[g] >> lane) & 1u)) return;  // finished (or padding) frames keep their messages untouched
-
-    const int e0 = EXACT ? i * DC : row_ptr[i];
-    const int deg = EXACT ? DC : (row_ptr[i + 1] - e0);
-    T *base = msg + ((size_t)g * E + e0) * kFG + lane;
-
-    T d[DC];
-#pragma unroll
-    for (int k = 0; k < DC; k++) {
-        if (EXACT || k < deg) {
-            if (FIRST) d[k] = __ldg(lratio + ((size_t)g * N + __ldg(col_idx + e0 + k)) * kFG + lane);
-            else d[k] = ld_stream(base + (size_t)k * kFG);
-        }
-    }
-
+__device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const T *lr_lane, const int32_t *cols) {
     constexpr int NB = (DC + 7) / 8;
     T ck[NB];
     T B = T(1);
@@ -86,10 +64,9 @@ row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_
         B = mul_rn(B, dk);
     }
     if (bad) {  // invalid likelihood ratios (negative / NaN): redo this check with full IEEE divisions, nothing stored yet
-        row_slow_path<T, FIRST>(base, lratio + (size_t)g * N * kFG + lane, col_idx + e0, deg);
+        row_slow_path<T, FIRST>(base, lr_lane, cols, deg);
         return;
     }
-
     T F = T(1);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
@@ -109,6 +86,136 @@ row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_
     }
 }
 
+// Variant A: one warp per (check, group), loads straight into registers. Used for small or sparsely active waves
+// (finished lanes load nothing, so a group with one straggler moves one 32 B sector per edge, not 256 B).
+template <typename T, int DC, bool EXACT, bool FIRST, int kRowWarps>
+__global__ void __launch_bounds__(kRowWarps * 32)
+row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
+                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (item >= (long long)G * M) return;
+    const int gl = (int)(item / M), i = (int)(item - (long long)gl * M);
+    const int g = g0 + gl;
+    if (!((actw[g] >> lane) & 1u)) return;  // finished (or padding) frames keep their messages untouched
+
+    const int e0 = EXACT ? i * DC : row_ptr[i];
+    const int deg = EXACT ? DC : (row_ptr[i + 1] - e0);
+    T *base = msg + ((size_t)g * E + e0) * kFG + lane;
+
+    T d[DC];
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < deg) {
+            if (FIRST) d[k] = __ldg(lratio + ((size_t)g * N + __ldg(col_idx + e0 + k)) * kFG + lane);
+            else d[k] = ld_stream(base + (size_t)k * kFG);
+        }
+    }
+    row_compute<T, DC, EXACT, FIRST>(d, deg, base, lratio + (size_t)g * N * kFG + lane, col_idx + e0);
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on the mbarrier as transferred bytes
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Variant B (bulk path; opt-in with DNALDPC_ROW_IMPL=tma): persistent warps, each owning one shared-memory tile. While a warp computes check t
+// from registers, the TMA engine streams the 18 KB of its next check (DC x 32 frames, contiguous in `msg`) into the
+// tile with one cp.async.bulk; the loads never occupy registers or LSU slots and their latency hides behind ~3 000
+// cycles of fp64 work. FIRST gathers the DC 256-byte lratio segments with one bulk copy per edge instead.
+// Measured on B200 (round 1, 4096-frame wave): 1.95 ms per launch vs 1.75-1.79 ms for variant A, because the check-node
+// pass is limited by how many bytes an SM can keep in flight (registers + smem are exhausted by the 72 live factors),
+// not by exposed load latency; a plain copy with this access pattern needs ~290 KB in flight per SM to reach 6.8 TB/s
+// and gets 5.5 TB/s with the 147 KB that 8 warps can hold. Kept as the measured alternative, not the default.
+constexpr int kRowTmaWarps = 4;
+
+template <typename T, int DC, bool EXACT, bool FIRST>
+__global__ void __launch_bounds__(kRowTmaWarps * 32, 2)
+row_pass_tma_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
+                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRowTmaWarps * DC * kFG * sizeof(T)) + warp;
+    const long long total = (long long)G * M;
+    const long long stride = (long long)gridDim.x * kRowTmaWarps;
+    long long item = (long long)blockIdx.x * kRowTmaWarps + warp;
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    const uint64_t pol = l2_evict_first_policy();
+
+    auto issue = [&](long long it) {  // whole warp calls; no-op for groups with no active frame
+        const int gl = (int)(it / M), i = (int)(it - (long long)gl * M);
+        const int g = g0 + gl;
+        if (__ldg(actw + g) == 0) return;
+        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
+        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
+        if (deg == 0) return;
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
+        if (FIRST) {
+            __syncwarp();
+            for (int k = lane; k < deg; k += 32)
+                tma_load_1d(tile + (size_t)k * kFG, lratio + ((size_t)g * N + __ldg(col_idx + e0 + k)) * kFG,
+                            (uint32_t)(kFG * sizeof(T)), bar, pol);
+        } else if (lane == 0) {
+            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar, pol);
+        }
+    };
+
+    if (item < total) issue(item);
+    uint32_t parity = 0;
+    for (; item < total; item += stride) {
+        const int gl = (int)(item / M), i = (int)(item - (long long)gl * M);
+        const int g = g0 + gl;
+        const uint32_t act = __ldg(actw + g);
+        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
+        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
+        const bool on = (act >> lane) & 1u;
+        T d[DC];
+        if (act != 0 && deg != 0) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+#pragma unroll
+            for (int k = 0; k < DC; k++)
+                if (EXACT || k < deg) d[k] = tile[k * kFG + lane];
+            __syncwarp();                       // every lane has its registers: the tile may be overwritten
+            if (lane == 0) fence_proxy_async_smem();
+        }
+        if (item + stride < total) issue(item + stride);
+        if (on && deg != 0) {
+            T *base = msg + ((size_t)g * E + e0) * kFG + lane;
+            row_compute<T, DC, EXACT, FIRST>(d, deg, base, lratio + (size_t)g * N * kFG + lane, col_idx + e0);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bit-node (column) pass, dec.cpp:667-693.  One thread = one (bit j, frame f); one warp = bit j of 32 frames.
 //   P_0 = lratio_j, P_{k+1} = P_k*lr_k; tot = P_last (NaN -> 1); dblk_j = (tot <= 1);
@@ -121,9 +228,9 @@ template <typename T, int DV, bool EXACT>
 __global__ void __launch_bounds__(kColWarps * 32)
 col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__restrict__ decw,
                 const uint32_t *__restrict__ actw, T *__restrict__ post, const int32_t *__restrict__ col_ptr,
-                const int32_t *__restrict__ col_edge, int N, int E, int cols_per_warp) {
+                const int32_t *__restrict__ col_edge, int N, int E, int g0, int cols_per_warp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
+    const int g = g0 + blockIdx.y;
     const uint32_t act = actw[g];
     if (act == 0) return;
     const bool on = (act >> lane) & 1u;
@@ -174,31 +281,51 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
 // their iteration count n (the value Run_Belief_Propagation_Decoder returns).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSynThreads = 256;
+constexpr int kSynSplit = 8;  // CTAs per group (row chunks); the last one to arrive applies the loop control
 
 __global__ void __launch_bounds__(kSynThreads)
 syndrome_update_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ actw, int32_t *__restrict__ iters,
                        uint8_t *__restrict__ okflag, const int32_t *__restrict__ row_ptr,
-                       const int32_t *__restrict__ col_idx, int M, int N, int n, int max_iter,
+                       const int32_t *__restrict__ col_idx, uint32_t *__restrict__ unsatw,
+                       unsigned int *__restrict__ arrive, int M, int N, int g0, int n, int max_iter,
                        unsigned int *__restrict__ n_active /* counter of this iteration */) {
-    const int g = blockIdx.x;
+    const int g = g0 + blockIdx.y;
     const uint32_t act = actw[g];
-    if (act == 0) return;
+    if (act == 0) return;  // uniform over the kSynSplit CTAs of the group: actw only changes in the last arriver
     const uint32_t *dw = decw + (size_t)g * N;
+    const int rows_per = (M + kSynSplit - 1) / kSynSplit;
+    const int i_end = min(M, (int)(blockIdx.x + 1) * rows_per);
     uint32_t acc = 0;
-    for (int i = threadIdx.x; i < M; i += kSynThreads) {
+    for (int i = blockIdx.x * rows_per + threadIdx.x; i < i_end; i += kSynThreads) {
         uint32_t p = 0;
         const int e1 = __ldg(row_ptr + i + 1);
-        for (int e = __ldg(row_ptr + i); e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
+        int e = __ldg(row_ptr + i);
+        for (; e + 4 <= e1; e += 4) {  // 4 independent gathers in flight
+            const uint32_t a = __ldg(dw + __ldg(col_idx + e)), b = __ldg(dw + __ldg(col_idx + e + 1));
+            const uint32_t c = __ldg(dw + __ldg(col_idx + e + 2)), d = __ldg(dw + __ldg(col_idx + e + 3));
+            p ^= (a ^ b) ^ (c ^ d);
+        }
+        for (; e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
         acc |= p;
     }
     acc = __reduce_or_sync(0xffffffffu, acc);
     __shared__ uint32_t s_or[kSynThreads / 32];
+    __shared__ unsigned int s_ticket;
     if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t unsat = 0;
+    if (threadIdx.x == 0) {
+        uint32_t part = 0;
 #pragma unroll
-        for (int w = 0; w < kSynThreads / 32; w++) unsat |= s_or[w];
+        for (int w = 0; w < kSynThreads / 32; w++) part |= s_or[w];
+        if (part) atomicOr(unsatw + g, part);
+        __threadfence();
+        s_ticket = atomicAdd(arrive + g, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != kSynSplit - 1) return;
+    if (threadIdx.x < 32) {  // last CTA of the group: every partial OR is visible
+        __threadfence();
+        const uint32_t unsat = *((volatile uint32_t *)(unsatw + g));
         const uint32_t done_ok = act & ~unsat;
         const uint32_t still = (n >= max_iter) ? 0u : (act & unsat);
         const uint32_t done = act & ~still;
@@ -209,6 +336,8 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__
         }
         if (f == 0) {
             actw[g] = still;
+            unsatw[g] = 0;  // re-armed for the next iteration
+            arrive[g] = 0;
             if (still) atomicAdd(n_active, (unsigned)__popc(still));
         }
     }
@@ -281,10 +410,13 @@ setup_kernel(SetupArgs a, T *__restrict__ lratio, uint32_t *__restrict__ decw, i
     }
 }
 
-__global__ void init_state_kernel(uint32_t *actw, int32_t *iters, uint8_t *okflag, int G, int nframes) {
+__global__ void init_state_kernel(uint32_t *actw, uint32_t *unsatw, unsigned int *arrive, int32_t *iters, uint8_t *okflag,
+                                  int G, int nframes) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < G * kFG) { iters[t] = 0; okflag[t] = 0; }
     if (t < G) {
+        unsatw[t] = 0;
+        arrive[t] = 0;
         const long long lo = (long long)t * kFG;
         const long long cnt = (long long)nframes - lo;
         actw[t] = cnt >= 32 ? 0xffffffffu : (cnt <= 0 ? 0u : ((1u << cnt) - 1u));

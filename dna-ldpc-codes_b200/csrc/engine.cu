@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bp_kernels.cuh"
@@ -60,34 +61,44 @@ Engine::Engine(const Code &code, int device, int precision, int wave_frames)
     up(&d_col_ptr_, code.col_ptr);
     up(&d_col_edge_, code.col_edge);
     chk(cudaMalloc((void **)&d_table_, 256 * sizeof(double)), "cudaMalloc(table)");
-    for (auto &e : ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    chk(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_), "cudaDeviceGetAttribute");
+    for (auto &h : ev_) for (auto &e : h) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    chk(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming), "cudaEventCreate");
+    for (auto &e : join_ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     for (auto &e : prof_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
     chk(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto &st : sub_) chk(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
 Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_actw_,
-                    d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
+                    d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_, d_unsatw_, d_arrive_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
-    for (auto &e : ev_) if (e) cudaEventDestroy(e);
+    for (auto &h : ev_) for (auto &e : h) if (e) cudaEventDestroy(e);
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
+    for (auto &e : join_ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
+    for (auto &st : sub_) if (st) cudaStreamDestroy(st);
 }
 
 int Engine::ensure_wave(int nf, bool want_post) {
     const int G = (nf + 31) / 32;
     if (G > cap_groups_) {
-        void *ptrs[] = {d_msg_, d_lratio_, d_post_, d_decw_, d_actw_, d_iters_, d_ok_};
+        void *ptrs[] = {d_msg_, d_lratio_, d_post_, d_decw_, d_actw_, d_iters_, d_ok_, d_unsatw_, d_arrive_};
         for (void *p : ptrs) if (p) cudaFree(p);
-        d_msg_ = d_lratio_ = d_post_ = nullptr; d_decw_ = d_actw_ = nullptr; d_iters_ = nullptr; d_ok_ = nullptr;
+        d_msg_ = d_lratio_ = d_post_ = nullptr; d_decw_ = d_actw_ = d_unsatw_ = nullptr; d_iters_ = nullptr; d_ok_ = nullptr;
+        d_arrive_ = nullptr;
         cap_groups_ = 0;
         CK(cudaMalloc(&d_msg_, std::max<size_t>((size_t)G * E_ * kFG * esz_, 16)));
         CK(cudaMalloc(&d_lratio_, (size_t)G * N_ * kFG * esz_));
         CK(cudaMalloc((void **)&d_decw_, (size_t)G * N_ * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&d_actw_, (size_t)G * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&d_unsatw_, (size_t)G * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&d_arrive_, (size_t)G * sizeof(unsigned)));
         CK(cudaMalloc((void **)&d_iters_, (size_t)G * kFG * sizeof(int32_t)));
         CK(cudaMalloc((void **)&d_ok_, (size_t)G * kFG));
         cap_groups_ = G;
@@ -97,7 +108,7 @@ int Engine::ensure_wave(int nf, bool want_post) {
 }
 
 int Engine::ensure_counters(int max_iter) {
-    const int need = max_iter + 2;
+    const int need = kHalves * (max_iter + 2);
     if (need > cap_counters_) {
         if (d_counters_) cudaFree(d_counters_);
         if (h_counters_) cudaFreeHost(h_counters_);
@@ -112,18 +123,36 @@ int Engine::ensure_counters(int max_iter) {
 // ---- kernel dispatch -----------------------------------------------------------------------------
 
 template <typename T, int DC, bool EXACT>
-static void launch_row_t(bool first, T *msg, const T *lratio, const uint32_t *actw, const int32_t *row_ptr,
-                         const int32_t *col_idx, int M, int N, int E, int G, cudaStream_t st) {
+static void launch_row_t(bool first, bool bulk, int sm_count, T *msg, const T *lratio, const uint32_t *actw,
+                         const int32_t *row_ptr, const int32_t *col_idx, int M, int N, int E, int g0, int G, cudaStream_t st) {
     const long long items = (long long)G * M;
-    const unsigned grid = (unsigned)((items + kRowWarps - 1) / kRowWarps);
-    if (first) row_pass_kernel<T, DC, EXACT, true><<<grid, kRowWarps * 32, 0, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, G);
-    else row_pass_kernel<T, DC, EXACT, false><<<grid, kRowWarps * 32, 0, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, G);
+    if (bulk) {  // persistent TMA-prefetch variant: two CTAs of 4 warps per SM, one 18 KB tile per warp
+        const size_t smem = (size_t)kRowTmaWarps * DC * kFG * sizeof(T) + kRowTmaWarps * sizeof(uint64_t);
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[first]) {
+            if (first) cudaFuncSetAttribute(row_pass_tma_kernel<T, DC, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else cudaFuncSetAttribute(row_pass_tma_kernel<T, DC, EXACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set[first] = true;
+        }
+        const int per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
+        const long long want = (items + kRowTmaWarps - 1) / kRowTmaWarps;
+        const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * per_sm, want);
+        if (first) row_pass_tma_kernel<T, DC, EXACT, true><<<grid, kRowTmaWarps * 32, smem, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, g0, G);
+        else row_pass_tma_kernel<T, DC, EXACT, false><<<grid, kRowTmaWarps * 32, smem, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, g0, G);
+        return;
+    }
+    const unsigned grid = (unsigned)((items + 3) / 4);
+    if (first) row_pass_kernel<T, DC, EXACT, true, 4><<<grid, 128, 0, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, g0, G);
+    else row_pass_kernel<T, DC, EXACT, false, 4><<<grid, 128, 0, st>>>(msg, lratio, actw, row_ptr, col_idx, M, N, E, g0, G);
 }
 
-template <typename T> int Engine::launch_row(bool first, int G, cudaStream_t st) {
+template <typename T> int Engine::launch_row(bool first, int g0, int G, bool dense, cudaStream_t st) {
     T *msg = (T *)d_msg_;
     const T *lr = (const T *)d_lratio_;
-#define ROW(DC, EX) launch_row_t<T, DC, EX>(first, msg, lr, d_actw_, d_row_ptr_, d_col_idx_, M_, N_, E_, G, st)
+    // bulk (TMA) variant for full, large waves; register-load variant when few frames are left or the wave is small
+    static const int force = [] { const char *e = getenv("DNALDPC_ROW_IMPL"); return !e ? 0 : (!strcmp(e, "ldg") ? 1 : (!strcmp(e, "tma") ? 2 : 0)); }();
+    const bool bulk = force == 2 && (long long)G * M_ >= 4LL * sm_count_ * 8 && dense;
+#define ROW(DC, EX) launch_row_t<T, DC, EX>(first, bulk, sm_count_, msg, lr, d_actw_, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, st)
     if (reg_rows_ && max_row_deg_ == 72) ROW(72, true);
     else if (max_row_deg_ <= 8) ROW(8, false);
     else if (max_row_deg_ <= 32) ROW(32, false);
@@ -137,17 +166,17 @@ template <typename T> int Engine::launch_row(bool first, int G, cudaStream_t st)
 
 template <typename T, int DV, bool EXACT>
 static void launch_col_t(T *msg, const T *lratio, uint32_t *decw, const uint32_t *actw, T *post, const int32_t *col_ptr,
-                         const int32_t *col_edge, int N, int E, int G, cudaStream_t st) {
+                         const int32_t *col_edge, int N, int E, int g0, int G, cudaStream_t st) {
     const int cpw = 8;  // columns per warp
     dim3 grid((unsigned)((N + kColWarps * cpw - 1) / (kColWarps * cpw)), (unsigned)G);
-    col_pass_kernel<T, DV, EXACT><<<grid, kColWarps * 32, 0, st>>>(msg, lratio, decw, actw, post, col_ptr, col_edge, N, E, cpw);
+    col_pass_kernel<T, DV, EXACT><<<grid, kColWarps * 32, 0, st>>>(msg, lratio, decw, actw, post, col_ptr, col_edge, N, E, g0, cpw);
 }
 
-template <typename T> int Engine::launch_col(int G, bool want_post, cudaStream_t st) {
+template <typename T> int Engine::launch_col(int g0, int G, bool want_post, cudaStream_t st) {
     T *msg = (T *)d_msg_;
     const T *lr = (const T *)d_lratio_;
     T *post = want_post ? (T *)d_post_ : nullptr;
-#define COL(DV, EX) launch_col_t<T, DV, EX>(msg, lr, d_decw_, d_actw_, post, d_col_ptr_, d_col_edge_, N_, E_, G, st)
+#define COL(DV, EX) launch_col_t<T, DV, EX>(msg, lr, d_decw_, d_actw_, post, d_col_ptr_, d_col_edge_, N_, E_, g0, G, st)
     if (reg_cols_ && max_col_deg_ == 8) COL(8, true);
     else if (reg_cols_ && max_col_deg_ == 3) COL(3, true);
     else if (max_col_deg_ <= 4) COL(4, false);
@@ -201,30 +230,56 @@ int Engine::run_wave(const dnaldpc_input &in, int nf, int max_iter, const dnaldp
         case DNALDPC_IN_VOTE_I8: launch_setup<T, IN_VOTE_I8>(a, lr, d_decw_, N_, G, st); break;
         default: return fail("unknown input kind", DNALDPC_ERR_ARG);
     }
-    init_state_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(d_actw_, d_iters_, d_ok_, G, nf);
+    init_state_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(d_actw_, d_unsatw_, d_arrive_, d_iters_, d_ok_, G, nf);
     stats.kernel_launches += 2;
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(d_counters_, 0, (size_t)(max_iter + 2) * sizeof(unsigned), st));
+    const int cstride = max_iter + 2;
+    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kHalves * cstride * sizeof(unsigned), st));
 
+    // Two halves of the wave iterate independently on their own streams (profiling mode: one half, one stream).
+    const int nh = (!profiling && G >= kHalves * kMinGroupsPerHalf) ? kHalves : 1;
+    int hg0[kHalves], hgn[kHalves];
+    cudaStream_t hs[kHalves];
+    bool live[kHalves], dense[kHalves];
+    for (int h = 0; h < nh; h++) {
+        dense[h] = true;
+        hg0[h] = (int)((long long)G * h / nh);
+        hgn[h] = (int)((long long)G * (h + 1) / nh) - hg0[h];
+        hs[h] = nh == 1 ? st : sub_[h];
+        live[h] = true;
+    }
+    if (nh > 1) {
+        CK(cudaEventRecord(fork_ev_, st));
+        for (int h = 0; h < nh; h++) CK(cudaStreamWaitEvent(hs[h], fork_ev_, 0));
+    }
     // dec.cpp:594-599: for (n = 0;; n++) { c = check(); if (n == max_iter || c == 0) break; iterate; }
     for (int n = 0;; n++) {
-        syndrome_update_kernel<<<G, kSynThreads, 0, st>>>(d_decw_, d_actw_, d_iters_, d_ok_, d_row_ptr_, d_col_idx_, M_,
-                                                          N_, n, max_iter, d_counters_ + n);
-        stats.kernel_launches++;
-        CK(cudaGetLastError());
-        if (n == max_iter) break;
-        CK(cudaMemcpyAsync(h_counters_ + n, d_counters_ + n, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(ev_[n % (kLag + 1)], st));
-        if (n >= kLag) {  // lagged poll: the host runs at most kLag iterations ahead of the device
-            CK(cudaEventSynchronize(ev_[(n - kLag) % (kLag + 1)]));
-            if (h_counters_[n - kLag] == 0) break;  // every frame finished: later launches are no-ops
+        bool any = false;
+        for (int h = 0; h < nh; h++) {
+            if (!live[h]) continue;
+            unsigned *cnt = d_counters_ + (size_t)h * cstride + n;
+            syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)hgn[h]), kSynThreads, 0, hs[h]>>>(
+                d_decw_, d_actw_, d_iters_, d_ok_, d_row_ptr_, d_col_idx_, d_unsatw_, d_arrive_, M_, N_, hg0[h], n, max_iter, cnt);
+            stats.kernel_launches++;
+            CK(cudaGetLastError());
+            if (n == max_iter) { live[h] = false; continue; }
+            CK(cudaMemcpyAsync(h_counters_ + (size_t)h * cstride + n, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, hs[h]));
+            CK(cudaEventRecord(ev_[h][n % (kLag + 1)], hs[h]));
+            if (n >= kLag) {  // lagged poll: the host runs at most kLag iterations ahead of the device
+                CK(cudaEventSynchronize(ev_[h][(n - kLag) % (kLag + 1)]));
+                const unsigned left = h_counters_[(size_t)h * cstride + n - kLag];
+                if (left == 0) { live[h] = false; continue; }  // later launches are no-ops
+                dense[h] = (long long)left * 2 >= (long long)hgn[h] * kFG;  // at least half of the frames still iterate
+            }
+            any = true;
         }
+        if (!any) break;
         if (profiling) CK(cudaEventRecord(prof_ev_[0], st));
-        rc = launch_row<T>(n == 0, G, st);
-        if (rc) return rc;
+        for (int h = 0; h < nh; h++)
+            if (live[h]) { rc = launch_row<T>(n == 0, hg0[h], hgn[h], dense[h], hs[h]); if (rc) return rc; }
         if (profiling) CK(cudaEventRecord(prof_ev_[1], st));
-        rc = launch_col<T>(G, want_post, st);
-        if (rc) return rc;
+        for (int h = 0; h < nh; h++)
+            if (live[h]) { rc = launch_col<T>(hg0[h], hgn[h], want_post, hs[h]); if (rc) return rc; }
         if (profiling) {
             CK(cudaEventRecord(prof_ev_[2], st));
             CK(cudaEventSynchronize(prof_ev_[2]));
@@ -233,6 +288,12 @@ int Engine::run_wave(const dnaldpc_input &in, int nf, int max_iter, const dnaldp
             cudaEventElapsedTime(&b_ms, prof_ev_[1], prof_ev_[2]);
             stats.row_ms += a_ms;
             stats.col_ms += b_ms;
+        }
+    }
+    if (nh > 1) {
+        for (int h = 0; h < nh; h++) {
+            CK(cudaEventRecord(join_ev_[h], hs[h]));
+            CK(cudaStreamWaitEvent(st, join_ev_[h], 0));
         }
     }
 

@@ -34,8 +34,8 @@ class Engine {
   private:
     template <typename T> int run_wave(const dnaldpc_input &in_dev, int nf, int max_iter, const dnaldpc_output &out_dev,
                                        cudaStream_t st);
-    template <typename T> int launch_row(bool first, int G, cudaStream_t st);
-    template <typename T> int launch_col(int G, bool want_post, cudaStream_t st);
+    template <typename T> int launch_row(bool first, int g0, int G, bool dense, cudaStream_t st);
+    template <typename T> int launch_col(int g0, int G, bool want_post, cudaStream_t st);
     int ensure_wave(int nf, bool want_post);
     int ensure_counters(int max_iter);
     int fail(cudaError_t e, const char *what);
@@ -43,7 +43,7 @@ class Engine {
     void *stage(void **buf, size_t *cap, size_t need);
 
     std::string err_;
-    int device_ = 0, precision_ = 0, wave_frames_ = 4096;
+    int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
     size_t esz_ = 8;
@@ -52,16 +52,22 @@ class Engine {
     // wave state (device)
     int cap_groups_ = 0;
     void *d_msg_ = nullptr, *d_lratio_ = nullptr, *d_post_ = nullptr;
-    uint32_t *d_decw_ = nullptr, *d_actw_ = nullptr;
+    uint32_t *d_decw_ = nullptr, *d_actw_ = nullptr, *d_unsatw_ = nullptr;
+    unsigned int *d_arrive_ = nullptr;
     int32_t *d_iters_ = nullptr;
     uint8_t *d_ok_ = nullptr;
     double *d_table_ = nullptr;  // 256 doubles (BSC uses the first 2)
     unsigned int *d_counters_ = nullptr, *h_counters_ = nullptr;
     int cap_counters_ = 0;
     static constexpr int kLag = 2;
-    cudaEvent_t ev_[kLag + 1] = {};
+    // A wave is split into two halves of groups that iterate on their own streams: the tail of one half's kernel
+    // is filled by the other half's next kernel (groups are independent, so no barrier is needed between them).
+    static constexpr int kHalves = 2;
+    static constexpr int kMinGroupsPerHalf = 16;
+    cudaEvent_t ev_[kHalves][kLag + 1] = {};
+    cudaEvent_t fork_ev_ = nullptr, join_ev_[kHalves] = {};
     cudaEvent_t prof_ev_[3] = {};
-    cudaStream_t own_stream_ = nullptr;
+    cudaStream_t own_stream_ = nullptr, sub_[kHalves] = {};
     // staging for the host-pointer path (device side)
     void *s_in_ = nullptr, *s_bits_ = nullptr, *s_dblk_ = nullptr, *s_post_ = nullptr, *s_pchk_ = nullptr;
     size_t c_in_ = 0, c_bits_ = 0, c_dblk_ = 0, c_post_ = 0, c_pchk_ = 0;
