@@ -1,12 +1,15 @@
 // bp_kernels.cuh - hand-written sm_100a kernels of the flooding sum-product decoder.
 //
-// Data layout in HBM (one "wave" = G groups of 32 frames, frame-interleaved so that a warp = 32 frames of a group):
+// Data layout in HBM. The decoder owns S = 32*G "slots" (G groups of 32); a slot holds one frame from the moment it is
+// admitted until its syndrome is zero (or max_iter is hit), then it is harvested and refilled with the next pending
+// frame ("continuous batching": every warp lane keeps doing useful work although frames need different iteration
+// counts). A warp is always "one node x the 32 slots of a group":
 //   msg   [G][E][32] T     ONE in-place message per edge: holds pr (bit->check, p0/p1) before the check-node pass
 //                          and lr (check->bit) after it. Edge order = CSR (row-major, ascending column), so the 72
-//                          messages x 32 frames of a check are one contiguous 18 KB chunk.
+//                          messages x 32 slots of a check are one contiguous 18 KB run.
 //   lratio[G][N][32] T     channel likelihood ratios
-//   decw  [G][N]  u32      hard decisions, bit f of word = frame f of the group (warp ballot)
-//   actw  [G]     u32      frames of the group still iterating
+//   decw  [G][N]  u32      hard decisions, bit f of a word = slot f of the group (warp ballot)
+//   actw/donew/newfw/freshw/harvw [G] u32   slot state masks;  slot_frame/slot_iter [G*32]
 // Every global access of a warp is one fully used 256 B (fp64) / 128 B (fp32) segment.
 //
 // Reference semantics: Iter_Belief_Propagation dec.cpp:632-694, check() check.cpp:28-47,
@@ -19,26 +22,27 @@
 
 namespace dnaldpc {
 
-constexpr int kFG = 32;  // frames per group == warp width
+constexpr int kFG = 32;  // slots per group == warp width
 
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 template <typename T> __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
 
 // ------------------------------------------------------------------------------------------------
-// Check-node (row) pass, dec.cpp:644-662.  One thread = one (check i, frame f); one warp = check i of 32 frames.
+// Check-node (row) pass, dec.cpp:644-662.  One thread = one (check i, slot f); one warp = check i of 32 slots.
 //   d_k = 1 - 2/(1+pr_k);  F_0 = 1, F_{k+1} = F_k*d_k;  B_last = 1, B_{k-1} = B_k*d_k;  lr_k = (1+F_k*B_k)/(1-F_k*B_k)
 // The reference evaluates d_k twice (identical values) and parks F_k in e->lr; here the d_k live in registers,
 // the backward products are check-pointed every 8 edges and re-derived block by block with the same
 // multiplications in the same order, so every rounded intermediate is the reference's.
-// FIRST: iteration 0 of a frame reads pr_e = lratio[col(e)] (Init_Belief_Propagation, dec.cpp:608-629) instead of msg,
-// which removes the E-sized initialisation write.
+// A FRESH slot (first iteration of its frame) reads pr_e = lratio[col(e)] (Init_Belief_Propagation, dec.cpp:608-629)
+// instead of msg, which removes the E-sized initialisation write.
 // ------------------------------------------------------------------------------------------------
-// Out-of-line fallback for one (check, frame) whose inputs left the proven operand ranges. Same operations in the
+
+// Out-of-line fallback for one (check, slot) whose inputs left the proven operand ranges. Same operations in the
 // same order as the reference, with nvcc's full-range divisions; F_k is re-derived for every k (O(deg^2)) because the
 // single in-place message array has no room to park it. Reached only with invalid (negative / NaN) likelihood ratios.
-template <typename T, bool FIRST>
-__device__ __noinline__ void row_slow_path(T *base, const T *lr_lane, const int32_t *cols, int deg) {
-    auto pr_at = [&](int k) -> T { return FIRST ? lr_lane[(size_t)cols[k] * kFG] : base[(size_t)k * kFG]; };
+template <typename T>
+__device__ __noinline__ void row_slow_path(T *base, const T *lr_lane, const int32_t *cols, int deg, bool fresh) {
+    auto pr_at = [&](int k) -> T { return fresh ? lr_lane[(size_t)cols[k] * kFG] : base[(size_t)k * kFG]; };
     T B = T(1);
     for (int k = deg - 1; k >= 0; k--) {
         T F = T(1);
@@ -49,9 +53,9 @@ __device__ __noinline__ void row_slow_path(T *base, const T *lr_lane, const int3
     }
 }
 
-// The arithmetic of one (check, frame): d[] holds pr_k on entry; writes lr_k to base[k*32]. One basic block.
-template <typename T, int DC, bool EXACT, bool FIRST>
-__device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const T *lr_lane, const int32_t *cols) {
+// The arithmetic of one (check, slot): d[] holds pr_k on entry; writes lr_k to base[k*32]. One basic block.
+template <typename T, int DC, bool EXACT>
+__device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const T *lr_lane, const int32_t *cols, bool fresh) {
     constexpr int NB = (DC + 7) / 8;
     T ck[NB];
     T B = T(1);
@@ -64,7 +68,7 @@ __device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const 
         B = mul_rn(B, dk);
     }
     if (bad) {  // invalid likelihood ratios (negative / NaN): redo this check with full IEEE divisions, nothing stored yet
-        row_slow_path<T, FIRST>(base, lr_lane, cols, deg);
+        row_slow_path<T>(base, lr_lane, cols, deg, fresh);
         return;
     }
     T F = T(1);
@@ -86,143 +90,96 @@ __device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const 
     }
 }
 
-// Variant A: one warp per (check, group), loads straight into registers. Used for small or sparsely active waves
-// (finished lanes load nothing, so a group with one straggler moves one 32 B sector per edge, not 256 B).
-template <typename T, int DC, bool EXACT, bool FIRST, int kRowWarps>
+// One (check i, slot f of group g): the DC loads go straight into the registers that then hold d_k, so all of them are
+// in flight at once. `mixed` (warp-uniform) = some lane of the warp starts a new frame and gathers lratio instead.
+template <typename T, int DC, bool EXACT>
+__device__ __forceinline__ void row_thread(T *__restrict__ msg, const T *__restrict__ lratio,
+                                           const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                           int N, int E, int g, int i, int f, bool fresh, bool mixed) {
+    const int e0 = EXACT ? i * DC : row_ptr[i];
+    const int deg = EXACT ? DC : (row_ptr[i + 1] - e0);
+    T *base = msg + ((size_t)g * E + e0) * kFG + f;
+    const T *lr_lane = lratio + (size_t)g * N * kFG + f;
+    T d[DC];
+    if (!mixed) {
+#pragma unroll
+        for (int k = 0; k < DC; k++)
+            if (EXACT || k < deg) d[k] = ld_stream(base + (size_t)k * kFG);
+    } else {  // a slot that starts a new frame: its pr_e is the channel ratio of the edge's bit
+#pragma unroll
+        for (int k = 0; k < DC; k++)
+            if (EXACT || k < deg) {
+                const T *src = fresh ? lr_lane + (size_t)__ldg(col_idx + e0 + k) * kFG : base + (size_t)k * kFG;
+                d[k] = *src;  // default cache policy: a bit's lratio is re-read by every check it belongs to
+            }
+    }
+    row_compute<T, DC, EXACT>(d, deg, base, lr_lane, col_idx + e0, fresh);
+}
+
+constexpr int kRowWarps = 4;
+
+// One warp per (check, group), lane = slot; every global access is one fully used 256 B segment.
+// (Measured alternative, removed: slot-major kernels - a warp = 32 checks of ONE slot - for groups thinned out in the
+// drain tail of a batch. All 32 lanes then do useful arithmetic, but every lane touches its own 32 B sector and L1
+// wavefront; on B200 that was 10-20 % slower end to end than letting thin groups run through this kernel.)
+template <typename T, int DC, bool EXACT>
 __global__ void __launch_bounds__(kRowWarps * 32)
 row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
+                const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr,
+                const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
     const int lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (item >= (long long)G * M) return;
     const int gl = (int)(item / M), i = (int)(item - (long long)gl * M);
     const int g = g0 + gl;
-    if (!((actw[g] >> lane) & 1u)) return;  // finished (or padding) frames keep their messages untouched
-
-    const int e0 = EXACT ? i * DC : row_ptr[i];
-    const int deg = EXACT ? DC : (row_ptr[i + 1] - e0);
-    T *base = msg + ((size_t)g * E + e0) * kFG + lane;
-
-    T d[DC];
-#pragma unroll
-    for (int k = 0; k < DC; k++) {
-        if (EXACT || k < deg) {
-            if (FIRST) d[k] = __ldg(lratio + ((size_t)g * N + __ldg(col_idx + e0 + k)) * kFG + lane);
-            else d[k] = ld_stream(base + (size_t)k * kFG);
-        }
-    }
-    row_compute<T, DC, EXACT, FIRST>(d, deg, base, lratio + (size_t)g * N * kFG + lane, col_idx + e0);
-}
-
-// ---- TMA (cp.async.bulk) + mbarrier helpers --------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// global -> shared bulk copy (SASS: UBLKCP), completion signalled on the mbarrier as transferred bytes
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Variant B (bulk path; opt-in with DNALDPC_ROW_IMPL=tma): persistent warps, each owning one shared-memory tile. While a warp computes check t
-// from registers, the TMA engine streams the 18 KB of its next check (DC x 32 frames, contiguous in `msg`) into the
-// tile with one cp.async.bulk; the loads never occupy registers or LSU slots and their latency hides behind ~3 000
-// cycles of fp64 work. FIRST gathers the DC 256-byte lratio segments with one bulk copy per edge instead.
-// Measured on B200 (round 1, 4096-frame wave): 1.95 ms per launch vs 1.75-1.79 ms for variant A, because the check-node
-// pass is limited by how many bytes an SM can keep in flight (registers + smem are exhausted by the 72 live factors),
-// not by exposed load latency; a plain copy with this access pattern needs ~290 KB in flight per SM to reach 6.8 TB/s
-// and gets 5.5 TB/s with the 147 KB that 8 warps can hold. Kept as the measured alternative, not the default.
-constexpr int kRowTmaWarps = 4;
-
-template <typename T, int DC, bool EXACT, bool FIRST>
-__global__ void __launch_bounds__(kRowTmaWarps * 32, 2)
-row_pass_tma_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                    const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRowTmaWarps * DC * kFG * sizeof(T)) + warp;
-    const long long total = (long long)G * M;
-    const long long stride = (long long)gridDim.x * kRowTmaWarps;
-    long long item = (long long)blockIdx.x * kRowTmaWarps + warp;
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncwarp();
-    const uint64_t pol = l2_evict_first_policy();
-
-    auto issue = [&](long long it) {  // whole warp calls; no-op for groups with no active frame
-        const int gl = (int)(it / M), i = (int)(it - (long long)gl * M);
-        const int g = g0 + gl;
-        if (__ldg(actw + g) == 0) return;
-        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
-        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
-        if (deg == 0) return;
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
-        if (FIRST) {
-            __syncwarp();
-            for (int k = lane; k < deg; k += 32)
-                tma_load_1d(tile + (size_t)k * kFG, lratio + ((size_t)g * N + __ldg(col_idx + e0 + k)) * kFG,
-                            (uint32_t)(kFG * sizeof(T)), bar, pol);
-        } else if (lane == 0) {
-            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar, pol);
-        }
-    };
-
-    if (item < total) issue(item);
-    uint32_t parity = 0;
-    for (; item < total; item += stride) {
-        const int gl = (int)(item / M), i = (int)(item - (long long)gl * M);
-        const int g = g0 + gl;
-        const uint32_t act = __ldg(actw + g);
-        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
-        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
-        const bool on = (act >> lane) & 1u;
-        T d[DC];
-        if (act != 0 && deg != 0) {
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-#pragma unroll
-            for (int k = 0; k < DC; k++)
-                if (EXACT || k < deg) d[k] = tile[k * kFG + lane];
-            __syncwarp();                       // every lane has its registers: the tile may be overwritten
-            if (lane == 0) fence_proxy_async_smem();
-        }
-        if (item + stride < total) issue(item + stride);
-        if (on && deg != 0) {
-            T *base = msg + ((size_t)g * E + e0) * kFG + lane;
-            row_compute<T, DC, EXACT, FIRST>(d, deg, base, lratio + (size_t)g * N * kFG + lane, col_idx + e0);
-        }
-    }
+    const uint32_t act = actw[g];
+    if (!((act >> lane) & 1u)) return;            // finished / empty slots keep their messages untouched
+    const uint32_t fw = freshw[g];                // warp-uniform
+    row_thread<T, DC, EXACT>(msg, lratio, row_ptr, col_idx, N, E, g, i, lane, (fw >> lane) & 1u, fw != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bit-node (column) pass, dec.cpp:667-693.  One thread = one (bit j, frame f); one warp = bit j of 32 frames.
+// Bit-node (column) pass, dec.cpp:667-693.  One thread = one (bit j, slot f).
 //   P_0 = lratio_j, P_{k+1} = P_k*lr_k; tot = P_last (NaN -> 1); dblk_j = (tot <= 1);
 //   S_last = 1, S_{k-1} = S_k*lr_k;  pr_k = P_k*S_k (NaN -> 1)
-// The hard decisions of the 32 frames are packed with one warp ballot.
+// Warp = bit j of the 32 slots of a group; the 32 hard decisions are packed with one warp ballot.
 // ------------------------------------------------------------------------------------------------
 constexpr int kColWarps = 8;
+
+template <typename T, int DV, bool EXACT>
+__device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restrict__ lratio, T *__restrict__ post,
+                                           const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
+                                           int N, int E, int g, int j, int f, bool on) {
+    const int c0 = EXACT ? j * DV : __ldg(col_ptr + j);
+    const int deg = EXACT ? DV : (__ldg(col_ptr + j + 1) - c0);
+    T *gmsg = msg + (size_t)g * E * kFG + f;
+    int eid[DV];
+#pragma unroll
+    for (int k = 0; k < DV; k++) eid[k] = (EXACT || k < deg) ? __ldg(col_edge + c0 + k) : 0;
+    T lr[DV];
+#pragma unroll
+    for (int k = 0; k < DV; k++) lr[k] = (on && (EXACT || k < deg)) ? ld_stream(gmsg + (size_t)eid[k] * kFG) : T(1);
+    T P = on ? __ldg(lratio + ((size_t)g * N + j) * kFG + f) : T(1);
+    T p[DV];
+#pragma unroll
+    for (int k = 0; k < DV; k++) {
+        p[k] = P;
+        if (EXACT || k < deg) P = mul_rn(P, lr[k]);
+    }
+    if (P != P) P = T(1);
+    if (post != nullptr && on) post[((size_t)g * N + j) * kFG + f] = P;
+    T S = T(1);
+#pragma unroll
+    for (int k = DV - 1; k >= 0; k--) {
+        if (EXACT || k < deg) {
+            T v = mul_rn(p[k], S);
+            if (v != v) v = T(1);
+            if (on) st_stream(gmsg + (size_t)eid[k] * kFG, v);
+            S = mul_rn(S, lr[k]);
+        }
+    }
+    return P <= T(1);
+}
 
 template <typename T, int DV, bool EXACT>
 __global__ void __launch_bounds__(kColWarps * 32)
@@ -234,38 +191,10 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
     const uint32_t act = actw[g];
     if (act == 0) return;
     const bool on = (act >> lane) & 1u;
-    T *gmsg = msg + (size_t)g * E * kFG + lane;
     const int jbeg = (blockIdx.x * kColWarps + warp) * cols_per_warp;
     const int jend = min(jbeg + cols_per_warp, N);
     for (int j = jbeg; j < jend; j++) {
-        const int c0 = EXACT ? j * DV : __ldg(col_ptr + j);
-        const int deg = EXACT ? DV : (__ldg(col_ptr + j + 1) - c0);
-        int eid[DV];
-#pragma unroll
-        for (int k = 0; k < DV; k++) eid[k] = (EXACT || k < deg) ? __ldg(col_edge + c0 + k) : 0;
-        T lr[DV];
-#pragma unroll
-        for (int k = 0; k < DV; k++) lr[k] = (on && (EXACT || k < deg)) ? ld_stream(gmsg + (size_t)eid[k] * kFG) : T(1);
-        T P = on ? __ldg(lratio + ((size_t)g * N + j) * kFG + lane) : T(1);
-        T p[DV];
-#pragma unroll
-        for (int k = 0; k < DV; k++) {
-            p[k] = P;
-            if (EXACT || k < deg) P = mul_rn(P, lr[k]);
-        }
-        if (P != P) P = T(1);
-        const bool bit = (P <= T(1));
-        if (post != nullptr && on) post[((size_t)g * N + j) * kFG + lane] = P;
-        T S = T(1);
-#pragma unroll
-        for (int k = DV - 1; k >= 0; k--) {
-            if (EXACT || k < deg) {
-                T v = mul_rn(p[k], S);
-                if (v != v) v = T(1);
-                if (on) st_stream(gmsg + (size_t)eid[k] * kFG, v);
-                S = mul_rn(S, lr[k]);
-            }
-        }
+        const bool bit = col_thread<T, DV, EXACT>(msg, lratio, post, col_ptr, col_edge, N, E, g, j, lane, on);
         const uint32_t w = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) {
             uint32_t *dst = decw + (size_t)g * N + j;
@@ -275,23 +204,83 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------
-// Syndrome + per-frame loop control (check.cpp:28-47 + dec.cpp:594-599). One CTA per group of 32 frames:
-// parity word of check i = XOR of the decision words of its bits (32 frames at once), OR-reduced over checks
-// with warp shuffles. Frames whose syndrome is zero, or that reached max_iter, leave the active mask and get
-// their iteration count n (the value Run_Belief_Propagation_Decoder returns).
+// Slot scheduler, part 1: admit pending frames into free slots (one warp per group, lane = slot).
+// Frames are taken from a single device-side counter, so any number of groups / streams / passes can pull from it.
+// Finished slots (donew) are handed to the harvest pass through harvw / harv_frame / harv_iter.
+// ------------------------------------------------------------------------------------------------
+struct SchedArrays {
+    uint32_t *actw, *donew, *newfw, *freshw, *harvw, *unsatw;
+    unsigned int *arrive;
+    int32_t *slot_frame, *slot_iter, *harv_frame, *harv_iter;
+    unsigned long long *next_frame;
+};
+
+__global__ void __launch_bounds__(256)
+assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsigned int *counter_to_zero) {
+    const int lane = threadIdx.x & 31;
+    const int gl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counter_to_zero) *counter_to_zero = 0;
+    if (gl >= G) return;
+    const int g = g0 + gl, slot = g * kFG + lane;
+    const uint32_t act = s.actw[g], done = s.donew[g];
+    if ((done >> lane) & 1u) {
+        s.harv_frame[slot] = s.slot_frame[slot];
+        s.harv_iter[slot] = s.slot_iter[slot];
+    }
+    const uint32_t free_mask = ~act;  // finished or empty slots
+    const int cnt = __popc(free_mask);
+    long long base = F;
+    if (lane == 0 && cnt > 0) {
+        const unsigned long long cur = *((volatile unsigned long long *)s.next_frame);
+        if ((long long)cur < F) base = (long long)atomicAdd(s.next_frame, (unsigned long long)cnt);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const bool is_free = (free_mask >> lane) & 1u;
+    const long long idx = base + __popc(free_mask & ((1u << lane) - 1u));
+    const bool take = is_free && idx < F;
+    const uint32_t newf = __ballot_sync(0xffffffffu, take);
+    if (take) { s.slot_frame[slot] = (int32_t)idx; s.slot_iter[slot] = 0; }
+    else if (is_free) s.slot_frame[slot] = -1;
+    if (lane == 0) {
+        s.actw[g] = act | newf;
+        s.donew[g] = 0;
+        s.newfw[g] = newf;
+        s.harvw[g] = done;
+        s.freshw[g] = (first_round ? 0u : s.freshw[g]) | newf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Syndrome + per-slot loop control (check.cpp:28-47 + dec.cpp:594-599). kSynSplit CTAs per group each XOR the
+// decision words of the bits of their checks (32 slots at once) and OR-reduce with warp shuffles; the last CTA to
+// arrive applies the control for the slots under consideration: syndrome zero -> done (success), iteration count ==
+// max_iter -> done (failure), else the slot iterates once more. The frame's n (the value
+// Run_Belief_Propagation_Decoder returns) and success flag are written by FRAME index.
+// `consider_new`: only slots admitted in this round are examined (the others were examined earlier this tick).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSynThreads = 256;
-constexpr int kSynSplit = 8;  // CTAs per group (row chunks); the last one to arrive applies the loop control
+constexpr int kSynSplit = 8;
 
 __global__ void __launch_bounds__(kSynThreads)
-syndrome_update_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ actw, int32_t *__restrict__ iters,
-                       uint8_t *__restrict__ okflag, const int32_t *__restrict__ row_ptr,
-                       const int32_t *__restrict__ col_idx, uint32_t *__restrict__ unsatw,
-                       unsigned int *__restrict__ arrive, int M, int N, int g0, int n, int max_iter,
-                       unsigned int *__restrict__ n_active /* counter of this iteration */) {
+syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t *__restrict__ iters_out,
+                       uint8_t *__restrict__ ok_out, const int32_t *__restrict__ row_ptr,
+                       const int32_t *__restrict__ col_idx, int M, int N, int g0, int max_iter, int consider_new,
+                       unsigned int *__restrict__ counter /* += slots still busy (active or awaiting harvest), or NULL */,
+                       long long F) {
     const int g = g0 + blockIdx.y;
-    const uint32_t act = actw[g];
-    if (act == 0) return;  // uniform over the kSynSplit CTAs of the group: actw only changes in the last arriver
+    const uint32_t act = s.actw[g];
+    const uint32_t consider = consider_new ? s.newfw[g] : act;
+    if (consider == 0) {  // uniform over the CTAs of the group: the masks only change in the last arriver
+        if (counter && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned add = (unsigned)(__popc(act) + __popc(s.donew[g]));
+            if (blockIdx.y == 0) {
+                const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
+                if (nx < F) add += (unsigned)min(F - nx, 1000000000LL);
+            }
+            if (add) atomicAdd(counter, add);
+        }
+        return;
+    }
     const uint32_t *dw = decw + (size_t)g * N;
     const int rows_per = (M + kSynSplit - 1) / kSynSplit;
     const int i_end = min(M, (int)(blockIdx.x + 1) * rows_per);
@@ -317,62 +306,68 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__
         uint32_t part = 0;
 #pragma unroll
         for (int w = 0; w < kSynThreads / 32; w++) part |= s_or[w];
-        if (part) atomicOr(unsatw + g, part);
+        if (part) atomicOr(s.unsatw + g, part);
         __threadfence();
-        s_ticket = atomicAdd(arrive + g, 1u);
+        s_ticket = atomicAdd(s.arrive + g, 1u);
     }
     __syncthreads();
     if (s_ticket != kSynSplit - 1) return;
     if (threadIdx.x < 32) {  // last CTA of the group: every partial OR is visible
         __threadfence();
-        const uint32_t unsat = *((volatile uint32_t *)(unsatw + g));
-        const uint32_t done_ok = act & ~unsat;
-        const uint32_t still = (n >= max_iter) ? 0u : (act & unsat);
-        const uint32_t done = act & ~still;
-        const int f = threadIdx.x;
+        const uint32_t unsat = *((volatile uint32_t *)(s.unsatw + g));
+        const int f = threadIdx.x, slot = g * kFG + f;
+        const bool mine = (consider >> f) & 1u;
+        const int it = mine ? s.slot_iter[slot] : 0;
+        const uint32_t maxed = __ballot_sync(0xffffffffu, mine && it >= max_iter);
+        const uint32_t done_ok = consider & ~unsat;
+        const uint32_t done = done_ok | (consider & maxed);
         if ((done >> f) & 1u) {
-            iters[(size_t)g * kFG + f] = n;
-            okflag[(size_t)g * kFG + f] = (uint8_t)((done_ok >> f) & 1u);
+            const int fr = s.slot_frame[slot];
+            iters_out[fr] = it;
+            ok_out[fr] = (uint8_t)((done_ok >> f) & 1u);
+        } else if (mine) {
+            s.slot_iter[slot] = it + 1;  // this slot runs one more iteration now
         }
         if (f == 0) {
-            actw[g] = still;
-            unsatw[g] = 0;  // re-armed for the next iteration
-            arrive[g] = 0;
-            if (still) atomicAdd(n_active, (unsigned)__popc(still));
+            const uint32_t still = act & ~done;
+            const uint32_t dn = s.donew[g] | done;
+            s.actw[g] = still;
+            s.donew[g] = dn;
+            s.unsatw[g] = 0;  // re-armed
+            s.arrive[g] = 0;
+            if (counter) {
+                unsigned add = (unsigned)(__popc(still) + __popc(dn));
+                if (blockIdx.y == 0) {
+                    const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
+                    if (nx < F) add += (unsigned)min(F - nx, 1000000000LL);
+                }
+                if (add) atomicAdd(counter, add);
+            }
         }
-    }
-}
-
-// Syndrome of the final decisions as 0/1 chars [F][M] (the `pchk` buffer of check(), check.cpp:28-47).
-__global__ void __launch_bounds__(256)
-syndrome_bytes_kernel(const uint32_t *__restrict__ decw, const int32_t *__restrict__ row_ptr,
-                      const int32_t *__restrict__ col_idx, int M, int N, int nframes, uint8_t *__restrict__ out) {
-    const int g = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    const uint32_t *dw = decw + (size_t)g * N;
-    uint32_t p = 0;
-    const int e1 = __ldg(row_ptr + i + 1);
-    for (int e = __ldg(row_ptr + i); e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
-    for (int f = 0; f < kFG; f++) {
-        const long long fr = (long long)g * kFG + f;
-        if (fr < nframes) out[(size_t)fr * M + i] = (uint8_t)((p >> f) & 1u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Likelihood setup ("channel options"): frame-major input of any kind -> lratio[G][N][32] + initial hard
-// decisions (lratio < 1, Init_Belief_Propagation dec.cpp:626) + loop state. A 32x32 tile is transposed through
-// shared memory so that both the frame-major reads and the frame-interleaved writes are coalesced.
+// Slot scheduler, part 2: harvest finished slots and set up newly admitted ones, one 32-bit x 32-slot tile per CTA.
+//  harvest : bit-transpose the ballot words back to the frame's outputs (packed bits / 0-1 chars / posterior)
+//  setup   : likelihood setup ("channel options") of the admitted frames: LR from {LR, LLR, BSC bits, AWGN y, vote
+//            counts} (DNA_main.cpp:1340-1345, channel.cpp:32-33,75-84, decoder.py:314), transposed through shared
+//            memory into the slot-interleaved lratio array, and the initial decision lratio < 1 (dec.cpp:626).
 // ------------------------------------------------------------------------------------------------
 enum InKind { IN_LR_F64 = 0, IN_LLR_F64 = 1, IN_BSC_BITS = 2, IN_AWGN_F32 = 3, IN_AWGN_F64 = 4, IN_VOTE_I8 = 5 };
 
 struct SetupArgs {
     const void *data;
     size_t frame_stride;  // bytes
-    double param;         // AWGN: 2/sigma^2 is NOT precomputed: LLR = 2*y/(sigma*sigma) like channel.cpp:32
+    double param;         // AWGN sigma: LLR = 2*y/(sigma*sigma) like channel.cpp:32
     const double *table;  // BSC: 2 entries, VOTE: 256 entries (device)
-    int nframes;          // valid frames of this wave
+};
+
+struct HarvestArgs {
+    uint32_t *bits;      // [F][wpf] or NULL
+    uint8_t *dblk;       // [F][N] or NULL
+    double *posterior;   // [F][N] or NULL
+    int wpf;
 };
 
 template <int KIND> __device__ __forceinline__ double load_lr(const SetupArgs &a, long long fr, int j) {
@@ -387,102 +382,99 @@ template <int KIND> __device__ __forceinline__ double load_lr(const SetupArgs &a
 
 template <typename T, int KIND>
 __global__ void __launch_bounds__(256)
-setup_kernel(SetupArgs a, T *__restrict__ lratio, uint32_t *__restrict__ decw, int N) {
+harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ lratio, const T *__restrict__ post,
+                     uint32_t *__restrict__ decw, int N, int g0) {
+    const int g = g0 + blockIdx.y;
+    const uint32_t hv = s.harvw[g], nf = s.newfw[g];
+    if ((hv | nf) == 0) return;
     __shared__ double tile[32][33];
-    const int g = blockIdx.y, j0 = blockIdx.x * 32;
+    __shared__ int s_new[32], s_old[32], s_oldit[32];
+    const int j0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {  // r = frame within the group, tx = bit within the tile
-        const long long fr = (long long)g * kFG + r;
-        const int j = j0 + tx;
-        double v = 1.0;                 // padding frames: erased, never active
-        if (fr < a.nframes && j < N) v = load_lr<KIND>(a, fr, j);
-        tile[r][tx] = v;
+    if (ty == 0) {
+        s_new[tx] = s.slot_frame[g * kFG + tx];
+        s_old[tx] = s.harv_frame[g * kFG + tx];
+        s_oldit[tx] = s.harv_iter[g * kFG + tx];
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {  // r = bit within the tile, tx = frame
-        const int j = j0 + r;
-        const T v = (T)tile[tx][r];
-        const uint32_t w = __ballot_sync(0xffffffffu, v < T(1));
-        if (j < N) {
-            lratio[((size_t)g * N + j) * kFG + tx] = v;
-            if (tx == 0) decw[(size_t)g * N + j] = w;
+    if (hv) {
+        const int j = j0 + tx;
+        const uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;  // tx = bit of the tile
+        if (h.bits && ty == 0) {
+            for (uint32_t m = hv; m; m &= m - 1) {
+                const int f = __ffs(m) - 1;
+                const uint32_t b = __ballot_sync(0xffffffffu, (word >> f) & 1u);
+                if (tx == 0) h.bits[(size_t)s_old[f] * h.wpf + blockIdx.x] = b;
+            }
+        }
+        if (h.dblk && j < N) {
+            for (int r = ty; r < 32; r += 8)
+                if ((hv >> r) & 1u) h.dblk[(size_t)s_old[r] * N + j] = (uint8_t)((word >> r) & 1u);
+        }
+        if (h.posterior) {
+            for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
+                const int jj = j0 + r;
+                double v = 0;
+                if (jj < N && ((hv >> tx) & 1u)) {
+                    const size_t idx = ((size_t)g * N + jj) * kFG + tx;
+                    v = s_oldit[tx] > 0 ? (double)post[idx] : (double)lratio[idx];
+                }
+                tile[r][tx] = v;
+            }
+            __syncthreads();
+            if (j < N)
+                for (int r = ty; r < 32; r += 8)  // r = slot, tx = bit
+                    if ((hv >> r) & 1u) h.posterior[(size_t)s_old[r] * N + j] = tile[tx][r];
+        }
+        __syncthreads();  // the old lratio / decw values have been read: the tile may be overwritten
+    }
+    if (nf) {
+        for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit of the tile
+            const int j = j0 + tx;
+            double v = 1.0;
+            if (((nf >> r) & 1u) && j < N) v = load_lr<KIND>(a, s_new[r], j);
+            tile[r][tx] = v;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
+            const int j = j0 + r;
+            const T v = (T)tile[tx][r];
+            const uint32_t w = __ballot_sync(0xffffffffu, v < T(1));
+            if (j < N) {
+                if ((nf >> tx) & 1u) lratio[((size_t)g * N + j) * kFG + tx] = v;
+                if (tx == 0) {
+                    uint32_t *dst = decw + (size_t)g * N + j;
+                    *dst = (*dst & ~nf) | (w & nf);
+                }
+            }
         }
     }
 }
 
-__global__ void init_state_kernel(uint32_t *actw, uint32_t *unsatw, unsigned int *arrive, int32_t *iters, uint8_t *okflag,
-                                  int G, int nframes) {
+// Syndrome of the final decisions of the slots being harvested, as 0/1 chars [F][M] (the `pchk` buffer of check()).
+__global__ void __launch_bounds__(256)
+syndrome_bytes_kernel(const uint32_t *__restrict__ decw, SchedArrays s, const int32_t *__restrict__ row_ptr,
+                      const int32_t *__restrict__ col_idx, int M, int N, int g0, uint8_t *__restrict__ out) {
+    const int g = g0 + blockIdx.y;
+    const uint32_t hv = s.harvw[g];
+    if (hv == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const uint32_t *dw = decw + (size_t)g * N;
+    uint32_t p = 0;
+    const int e1 = __ldg(row_ptr + i + 1);
+    for (int e = __ldg(row_ptr + i); e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
+    for (uint32_t m = hv; m; m &= m - 1) {
+        const int f = __ffs(m) - 1;
+        out[(size_t)s.harv_frame[g * kFG + f] * M + i] = (uint8_t)((p >> f) & 1u);
+    }
+}
+
+__global__ void init_sched_kernel(SchedArrays s, int G) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < G * kFG) { iters[t] = 0; okflag[t] = 0; }
-    if (t < G) {
-        unsatw[t] = 0;
-        arrive[t] = 0;
-        const long long lo = (long long)t * kFG;
-        const long long cnt = (long long)nframes - lo;
-        actw[t] = cnt >= 32 ? 0xffffffffu : (cnt <= 0 ? 0u : ((1u << cnt) - 1u));
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Result gather: bit-transpose the ballot words back to per-frame outputs.
-// ------------------------------------------------------------------------------------------------
-// packed bits [F][ceil(N/32)]: a warp takes 32 decision words (bits j0..j0+31 of 32 frames) and transposes 32x32 bits.
-__global__ void __launch_bounds__(256)
-gather_bits_kernel(const uint32_t *__restrict__ decw, int N, int nframes, int words_per_frame, size_t out_stride_words,
-                   uint32_t *__restrict__ out) {
-    const int g = blockIdx.y;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (w >= words_per_frame) return;
-    const int j = w * 32 + lane;
-    const uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int f = 0; f < 32; f++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (word >> f) & 1u);
-        if (lane == f) mine = b;
-    }
-    const long long fr = (long long)g * kFG + lane;
-    if (fr < nframes) out[(size_t)fr * out_stride_words + w] = mine;
-}
-
-// 0/1 chars [F][N] (the reference's `char *dblk`)
-__global__ void __launch_bounds__(256)
-gather_bytes_kernel(const uint32_t *__restrict__ decw, int N, int nframes, uint8_t *__restrict__ out) {
-    const int g = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    const uint32_t word = decw[(size_t)g * N + j];
-    for (int f = 0; f < kFG; f++) {
-        const long long fr = (long long)g * kFG + f;
-        if (fr < nframes) out[(size_t)fr * N + j] = (uint8_t)((word >> f) & 1u);
-    }
-}
-
-// posterior [F][N] double from post[G][N][32] (or from lratio for frames that never iterated)
-template <typename T>
-__global__ void __launch_bounds__(256)
-gather_posterior_kernel(const T *__restrict__ post, const T *__restrict__ lratio, const int32_t *__restrict__ iters,
-                        int N, int nframes, double *__restrict__ out) {
-    __shared__ double tile[32][33];
-    const int g = blockIdx.y, j0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const bool iterated = iters[(size_t)g * kFG + tx] > 0;
-    for (int r = ty; r < 32; r += 8) {  // r = bit, tx = frame
-        const int j = j0 + r;
-        double v = 0;
-        if (j < N) {
-            const size_t idx = ((size_t)g * N + j) * kFG + tx;
-            v = iterated ? (double)post[idx] : (double)lratio[idx];
-        }
-        tile[r][tx] = v;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {  // r = frame, tx = bit
-        const long long fr = (long long)g * kFG + r;
-        const int j = j0 + tx;
-        if (fr < nframes && j < N) out[(size_t)fr * N + j] = tile[tx][r];
-    }
+    if (t < G * kFG) { s.slot_frame[t] = -1; s.slot_iter[t] = 0; s.harv_frame[t] = -1; s.harv_iter[t] = 0; }
+    if (t < G) { s.actw[t] = 0; s.donew[t] = 0; s.newfw[t] = 0; s.freshw[t] = 0; s.harvw[t] = 0; s.unsatw[t] = 0; s.arrive[t] = 0; }
+    if (t == 0) *s.next_frame = 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
-// engine.h - per-device decoder engine: owns the device copies of the H edge tables, the frame-interleaved
-// message arrays of one wave, and the host-side iteration loop (early exit on zero syndrome / max_iter,
-// dec.cpp:594-599). Internal C++ interface behind the C ABI of include/dnaldpc.h.
+// engine.h - per-device decoder engine: owns the device copies of the H edge tables, the slot-interleaved message
+// arrays and the host side of the slot scheduler (admit -> syndrome/loop control -> check pass -> bit pass per tick;
+// early exit on zero syndrome / max_iter per frame, dec.cpp:594-599). Internal C++ interface behind include/dnaldpc.h.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -13,6 +13,8 @@
 
 namespace dnaldpc {
 
+struct SchedArrays;
+
 class Engine {
   public:
     Engine(const Code &code, int device, int precision, int wave_frames);
@@ -21,7 +23,7 @@ class Engine {
     const std::string &error() const { return err_; }
     int device() const { return device_; }
 
-    // DEVICE pointers in `in` / `out`; asynchronous on `stream` except for the lagged early-exit polls.
+    // DEVICE pointers in `in` / `out`; asynchronous on `stream` except for the lagged progress polls.
     int decode_device(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out, cudaStream_t stream);
     // HOST pointers; blocking.
     int decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out);
@@ -32,15 +34,16 @@ class Engine {
     bool profiling = false;
 
   private:
-    template <typename T> int run_wave(const dnaldpc_input &in_dev, int nf, int max_iter, const dnaldpc_output &out_dev,
-                                       cudaStream_t st);
-    template <typename T> int launch_row(bool first, int g0, int G, bool dense, cudaStream_t st);
+    template <typename T> int run(const dnaldpc_input &in_dev, int64_t F, int max_iter, const dnaldpc_output &out_dev, cudaStream_t st);
+    template <typename T> int launch_row(int g0, int G, cudaStream_t st);
     template <typename T> int launch_col(int g0, int G, bool want_post, cudaStream_t st);
-    int ensure_wave(int nf, bool want_post);
-    int ensure_counters(int max_iter);
+    template <typename T> int launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &out, int g0, int G, cudaStream_t st);
+    int ensure_slots(int groups, bool want_post);
+    int ensure_frame_scratch(int64_t F);
     int fail(cudaError_t e, const char *what);
     int fail(const std::string &m, int rc);
     void *stage(void **buf, size_t *cap, size_t need);
+    void fill_sched(SchedArrays &s) const;
 
     std::string err_;
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
@@ -49,22 +52,21 @@ class Engine {
     size_t esz_ = 8;
     // H edge tables (device)
     int32_t *d_row_ptr_ = nullptr, *d_col_idx_ = nullptr, *d_col_ptr_ = nullptr, *d_col_edge_ = nullptr;
-    // wave state (device)
+    // slot state (device)
     int cap_groups_ = 0;
     void *d_msg_ = nullptr, *d_lratio_ = nullptr, *d_post_ = nullptr;
-    uint32_t *d_decw_ = nullptr, *d_actw_ = nullptr, *d_unsatw_ = nullptr;
+    uint32_t *d_decw_ = nullptr, *d_masks_ = nullptr;  // masks: 6 words per group (act, done, newf, fresh, harv, unsat)
     unsigned int *d_arrive_ = nullptr;
-    int32_t *d_iters_ = nullptr;
+    int32_t *d_slot_ = nullptr;                          // 4 ints per slot (frame, iter, harv_frame, harv_iter)
+    unsigned long long *d_next_ = nullptr;
+    int32_t *d_iters_ = nullptr;                         // per-frame scratch when the caller does not want them
     uint8_t *d_ok_ = nullptr;
-    double *d_table_ = nullptr;  // 256 doubles (BSC uses the first 2)
+    int64_t cap_frames_ = 0;
+    double *d_table_ = nullptr;                          // 256 doubles (BSC uses the first 2)
+    // progress counters: ring per half, polled kLag ticks behind the device
+    static constexpr int kLag = 2, kRing = 16, kHalves = 2, kMinGroupsPerHalf = 16;
     unsigned int *d_counters_ = nullptr, *h_counters_ = nullptr;
-    int cap_counters_ = 0;
-    static constexpr int kLag = 2;
-    // A wave is split into two halves of groups that iterate on their own streams: the tail of one half's kernel
-    // is filled by the other half's next kernel (groups are independent, so no barrier is needed between them).
-    static constexpr int kHalves = 2;
-    static constexpr int kMinGroupsPerHalf = 16;
-    cudaEvent_t ev_[kHalves][kLag + 1] = {};
+    cudaEvent_t ev_[kHalves][kRing] = {};
     cudaEvent_t fork_ev_ = nullptr, join_ev_[kHalves] = {};
     cudaEvent_t prof_ev_[3] = {};
     cudaStream_t own_stream_ = nullptr, sub_[kHalves] = {};
