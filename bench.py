@@ -154,7 +154,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     code = ldpc.Code(PCHK)
-    dec = ldpc.Decoder(code, devices=[local], wave_frames=args.wave)
+    prec = ldpc.PREC_F32 if args.precision == "f32" else ldpc.PREC_F64
+    bscale = 0.5 if args.precision == "f32" else 1.0   # fp32 messages / ratios are 4 bytes
+    dec = ldpc.Decoder(code, devices=[local], wave_frames=args.wave, precision=prec)
     F = args.frames
     W = (N + 31) // 32
     frame0, _ = shard(F, rank)
@@ -245,16 +247,16 @@ def run_ours(args):
     row_ms, col_ms = st["row_ms"] / n_it, st["col_ms"] / n_it
     frames_per_launch = act_fi / n_it
     if row_ms >= col_ms:
-        kname, kms, kbytes = "row_pass_kernel (check-node)", row_ms, B_ROW * frames_per_launch
+        kname, kms, kbytes = "row_pass_kernel (check-node)", row_ms, bscale * B_ROW * frames_per_launch
     else:
-        kname, kms, kbytes = "col_pass_kernel (bit-node)", col_ms, B_COL * frames_per_launch
+        kname, kms, kbytes = "col_pass_kernel (bit-node)", col_ms, bscale * B_COL * frames_per_launch
     achieved = kbytes / (kms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src, "launch_ms": kms, "frames_per_launch": frames_per_launch,
             "row_ms": row_ms, "col_ms": col_ms,
-            "iteration": {"achieved": B_ITER * frames_per_launch / ((row_ms + col_ms) * 1e-3) / 1e9,
+            "iteration": {"achieved": bscale * B_ITER * frames_per_launch / ((row_ms + col_ms) * 1e-3) / 1e9,
                           "note": "B_iter=32E+8.25N per frame-iteration over row+col kernel time"},
-            "whole_step": {"achieved": B_ITER * (frame_iters_all / world) / (ms / args.steps * 1e-3) / 1e9,
+            "whole_step": {"achieved": bscale * B_ITER * (frame_iters_all / world) / (ms / args.steps * 1e-3) / 1e9,
                            "note": "B_iter x frame-iterations of a step / step time (all kernels, launch gaps included)"}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
@@ -273,7 +275,7 @@ def run_ours(args):
     line = {
         "metric": "decoded Gbit/s, n=18432 prprp", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, F),
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, F),
         "frame_iters_per_s": frame_iters_all * args.steps / (ms * 1e-3),
         "avg_iters": frame_iters_all / (world * F),
         "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": F * W * 4, "d2h_bytes_per_step": F * (W * 4 + 5),
@@ -299,6 +301,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-frames-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = bit-exact mode (the metric); f32 = optional fast mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

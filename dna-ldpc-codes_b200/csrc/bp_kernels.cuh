@@ -380,6 +380,8 @@ template <int KIND> __device__ __forceinline__ double load_lr(const SetupArgs &a
     return a.table[(int)((const int8_t *)row)[j] + 128];
 }
 
+constexpr int kHsTiles = 16;  // 32-bit tiles per CTA: keeps the (usually idle) launch down to a few thousand CTAs
+
 template <typename T, int KIND>
 __global__ void __launch_bounds__(256)
 harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ lratio, const T *__restrict__ post,
@@ -389,7 +391,6 @@ harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ 
     if ((hv | nf) == 0) return;
     __shared__ double tile[32][33];
     __shared__ int s_new[32], s_old[32], s_oldit[32];
-    const int j0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if (ty == 0) {
         s_new[tx] = s.slot_frame[g * kFG + tx];
@@ -397,56 +398,61 @@ harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ 
         s_oldit[tx] = s.harv_iter[g * kFG + tx];
     }
     __syncthreads();
-    if (hv) {
-        const int j = j0 + tx;
-        const uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;  // tx = bit of the tile
-        if (h.bits && ty == 0) {
-            for (uint32_t m = hv; m; m &= m - 1) {
-                const int f = __ffs(m) - 1;
-                const uint32_t b = __ballot_sync(0xffffffffu, (word >> f) & 1u);
-                if (tx == 0) h.bits[(size_t)s_old[f] * h.wpf + blockIdx.x] = b;
-            }
-        }
-        if (h.dblk && j < N) {
-            for (int r = ty; r < 32; r += 8)
-                if ((hv >> r) & 1u) h.dblk[(size_t)s_old[r] * N + j] = (uint8_t)((word >> r) & 1u);
-        }
-        if (h.posterior) {
-            for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
-                const int jj = j0 + r;
-                double v = 0;
-                if (jj < N && ((hv >> tx) & 1u)) {
-                    const size_t idx = ((size_t)g * N + jj) * kFG + tx;
-                    v = s_oldit[tx] > 0 ? (double)post[idx] : (double)lratio[idx];
+    const int ntiles = (N + 31) / 32;
+    for (int tile_id = blockIdx.x * kHsTiles; tile_id < min(ntiles, (int)(blockIdx.x + 1) * kHsTiles); tile_id++) {
+        const int j0 = tile_id * 32;
+        if (hv) {
+            const int j = j0 + tx;
+            const uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;  // tx = bit of the tile
+            if (h.bits && ty == 0) {
+                for (uint32_t m = hv; m; m &= m - 1) {
+                    const int f = __ffs(m) - 1;
+                    const uint32_t b = __ballot_sync(0xffffffffu, (word >> f) & 1u);
+                    if (tx == 0) h.bits[(size_t)s_old[f] * h.wpf + tile_id] = b;
                 }
+            }
+            if (h.dblk && j < N) {
+                for (int r = ty; r < 32; r += 8)
+                    if ((hv >> r) & 1u) h.dblk[(size_t)s_old[r] * N + j] = (uint8_t)((word >> r) & 1u);
+            }
+            if (h.posterior) {
+                for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
+                    const int jj = j0 + r;
+                    double v = 0;
+                    if (jj < N && ((hv >> tx) & 1u)) {
+                        const size_t idx = ((size_t)g * N + jj) * kFG + tx;
+                        v = s_oldit[tx] > 0 ? (double)post[idx] : (double)lratio[idx];
+                    }
+                    tile[r][tx] = v;
+                }
+                __syncthreads();
+                if (j < N)
+                    for (int r = ty; r < 32; r += 8)  // r = slot, tx = bit
+                        if ((hv >> r) & 1u) h.posterior[(size_t)s_old[r] * N + j] = tile[tx][r];
+            }
+            __syncthreads();  // the old lratio / decw values have been read: the tile may be overwritten
+        }
+        if (nf) {
+            for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit of the tile
+                const int j = j0 + tx;
+                double v = 1.0;
+                if (((nf >> r) & 1u) && j < N) v = load_lr<KIND>(a, s_new[r], j);
                 tile[r][tx] = v;
             }
             __syncthreads();
-            if (j < N)
-                for (int r = ty; r < 32; r += 8)  // r = slot, tx = bit
-                    if ((hv >> r) & 1u) h.posterior[(size_t)s_old[r] * N + j] = tile[tx][r];
-        }
-        __syncthreads();  // the old lratio / decw values have been read: the tile may be overwritten
-    }
-    if (nf) {
-        for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit of the tile
-            const int j = j0 + tx;
-            double v = 1.0;
-            if (((nf >> r) & 1u) && j < N) v = load_lr<KIND>(a, s_new[r], j);
-            tile[r][tx] = v;
-        }
-        __syncthreads();
-        for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
-            const int j = j0 + r;
-            const T v = (T)tile[tx][r];
-            const uint32_t w = __ballot_sync(0xffffffffu, v < T(1));
-            if (j < N) {
-                if ((nf >> tx) & 1u) lratio[((size_t)g * N + j) * kFG + tx] = v;
-                if (tx == 0) {
-                    uint32_t *dst = decw + (size_t)g * N + j;
-                    *dst = (*dst & ~nf) | (w & nf);
+            for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
+                const int j = j0 + r;
+                const T v = clamp_lr((T)tile[tx][r]);
+                const uint32_t w = __ballot_sync(0xffffffffu, v < T(1));
+                if (j < N) {
+                    if ((nf >> tx) & 1u) lratio[((size_t)g * N + j) * kFG + tx] = v;
+                    if (tx == 0) {
+                        uint32_t *dst = decw + (size_t)g * N + j;
+                        *dst = (*dst & ~nf) | (w & nf);
+                    }
                 }
             }
+            __syncthreads();  // before the next tile reuses the shared buffer
         }
     }
 }

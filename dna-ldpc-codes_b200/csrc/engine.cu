@@ -185,7 +185,7 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
         syndrome_bytes_kernel<<<grid, 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, M_, N_, g0, out.pchk);
         stats.kernel_launches++;
     }
-    dim3 grid((unsigned)((N_ + 31) / 32), (unsigned)G);
+    dim3 grid((unsigned)(((N_ + 31) / 32 + kHsTiles - 1) / kHsTiles), (unsigned)G);
     T *lr = (T *)d_lratio_;
     const T *post = (const T *)d_post_;
 #define HS(K) harvest_setup_kernel<T, K><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0)
