@@ -261,7 +261,7 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("row" if row_ms >= col_ms else "col")
+            roof["traffic"] = json.load(open(tr)).get("row_per_frame" if row_ms >= col_ms else "col_per_frame") * frames_per_launch
         except Exception:
             pass
 

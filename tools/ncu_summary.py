@@ -48,6 +48,7 @@ def main():
         sel = [x for x in rows if tag + "_pass" in x[idx['Kernel Name']]]
         if sel:
             tr[tag] = sum(tot(x) for x in sel) / len(sel)
+            tr[tag + "_per_frame"] = tr[tag] / frames
     tr["frames_per_launch"] = frames
     tr["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, " + os.path.relpath(out_md, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     json.dump(tr, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"), "w"), indent=1)
