@@ -16,6 +16,7 @@ OK = 0
 PREC_F64, PREC_F32 = 0, 1
 IN_LR_F64, IN_LLR_F64, IN_BSC_BITS, IN_AWGN_F32, IN_AWGN_F64, IN_VOTE_I8 = range(6)
 FLAG_HOST_EXP = 1
+FLAG_FIXED_ITERS = 2
 
 EXPORTS = [
     "dnaldpc_last_error", "dnaldpc_version", "dnaldpc_code_read_pchk", "dnaldpc_code_from_csr",
@@ -23,7 +24,7 @@ EXPORTS = [
     "dnaldpc_code_check_regular", "dnaldpc_decoder_create", "dnaldpc_decoder_destroy", "dnaldpc_decode_batch",
     "dnaldpc_decode_batch_device", "dnaldpc_run_bp_decoder", "dnaldpc_std_dev", "dnaldpc_vote_table",
     "dnaldpc_bsc_table", "dnaldpc_synth_bsc_device", "dnaldpc_get_stats", "dnaldpc_set_profiling",
-    "dnaldpc_selftest_math",
+    "dnaldpc_selftest_math", "dnaldpc_redecode_sweep",
 ]
 
 
@@ -89,6 +90,8 @@ def lib():
         L.dnaldpc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.dnaldpc_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.dnaldpc_selftest_math.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.dnaldpc_redecode_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.POINTER(Output), C.c_void_p]
         _lib = L
     return _lib
 
@@ -192,6 +195,20 @@ class Decoder:
         if "bits" in want:
             res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
                                         bitorder="little")[:, :N].astype(np.int8)
+        return res
+
+    def redecode_sweep(self, llr, max_iter, scales, flags=0):
+        """decoder.py:594-664 in one call: frames whose syndrome stays non-zero are re-decoded with LR = exp(scales[r]*LLR)."""
+        llr = np.ascontiguousarray(llr, dtype=np.float64)
+        scales = np.ascontiguousarray(scales, dtype=np.float64)
+        F, N = llr.shape
+        res = dict(bits_packed=np.zeros((F, self.words_per_frame), np.uint32), iters=np.zeros(F, np.int32),
+                   ok=np.zeros(F, np.uint8), rounds=np.zeros(F, np.int32))
+        out = Output(bits=res["bits_packed"].ctypes.data, iters=res["iters"].ctypes.data, is_codeword=res["ok"].ctypes.data)
+        _check(lib().dnaldpc_redecode_sweep(self._h, llr.ctypes.data, F, max_iter, scales.ctypes.data, len(scales), flags,
+                                            C.byref(out), res["rounds"].ctypes.data))
+        res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
+                                    bitorder="little")[:, :N].astype(np.int8)
         return res
 
     def run_bp_decoder(self, lratio, max_iter):

@@ -264,7 +264,7 @@ constexpr int kSynSplit = 8;
 __global__ void __launch_bounds__(kSynThreads)
 syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t *__restrict__ iters_out,
                        uint8_t *__restrict__ ok_out, const int32_t *__restrict__ row_ptr,
-                       const int32_t *__restrict__ col_idx, int M, int N, int g0, int max_iter, int consider_new,
+                       const int32_t *__restrict__ col_idx, int M, int N, int g0, int max_iter, int consider_new, int fixed_iters,
                        unsigned int *__restrict__ counter /* += slots still busy (active or awaiting harvest), or NULL */,
                        long long F) {
     const int g = g0 + blockIdx.y;
@@ -319,8 +319,9 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t
         const bool mine = (consider >> f) & 1u;
         const int it = mine ? s.slot_iter[slot] : 0;
         const uint32_t maxed = __ballot_sync(0xffffffffu, mine && it >= max_iter);
-        const uint32_t done_ok = consider & ~unsat;
-        const uint32_t done = done_ok | (consider & maxed);
+        // fixed_iters (Run_Belief_Propagation_Decoder_SAVE, dec.cpp:192-223): a zero syndrome does not stop the frame
+        const uint32_t done = fixed_iters ? (consider & maxed) : ((consider & ~unsat) | (consider & maxed));
+        const uint32_t done_ok = done & ~unsat;
         if ((done >> f) & 1u) {
             const int fr = s.slot_frame[slot];
             iters_out[fr] = it;
@@ -373,7 +374,7 @@ struct HarvestArgs {
 template <int KIND> __device__ __forceinline__ double load_lr(const SetupArgs &a, long long fr, int j) {
     const char *row = (const char *)a.data + (size_t)fr * a.frame_stride;
     if (KIND == IN_LR_F64) return ((const double *)row)[j];
-    if (KIND == IN_LLR_F64) return exp(((const double *)row)[j]);
+    if (KIND == IN_LLR_F64) return exp(a.param * ((const double *)row)[j]);  // param = LLR scale (1 unless re-decoding)
     if (KIND == IN_BSC_BITS) return a.table[(((const uint32_t *)row)[j >> 5] >> (j & 31)) & 1u];
     if (KIND == IN_AWGN_F32) return exp(2.0 * (double)((const float *)row)[j] / (a.param * a.param));
     if (KIND == IN_AWGN_F64) return exp(2.0 * ((const double *)row)[j] / (a.param * a.param));

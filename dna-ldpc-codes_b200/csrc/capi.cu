@@ -234,6 +234,65 @@ int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_ite
     return DNALDPC_OK;
 }
 
+int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
+                           int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds) {
+    if (!d || !llr || !out || !scales || n_scales <= 0 || F < 0) return set_err(DNALDPC_ERR_ARG, "bad argument");
+    const int M = d->c.M, N = d->c.N;
+    const size_t wpf = (size_t)(N + 31) / 32;
+    std::vector<uint8_t> ok((size_t)F, 0);
+    dnaldpc_input in{};
+    in.kind = DNALDPC_IN_LLR_F64;
+    in.flags = flags & (DNALDPC_FLAG_HOST_EXP | DNALDPC_FLAG_FIXED_ITERS);
+    in.data = llr;
+    in.param = scales[0];
+    dnaldpc_output o = *out;
+    o.is_codeword = ok.data();
+    int rc = dnaldpc_decode_batch(d, &in, F, max_iter, &o);  // round 0: every frame
+    if (rc) return rc;
+    if (rounds) for (int64_t f = 0; f < F; f++) rounds[f] = 0;
+    dnaldpc_stats total = d->stats;
+    std::vector<int64_t> failed;
+    for (int r = 1; r < n_scales; r++) {
+        failed.clear();
+        for (int64_t f = 0; f < F; f++) if (!ok[(size_t)f]) failed.push_back(f);
+        if (failed.empty()) break;
+        const size_t K = failed.size();
+        std::vector<double> sub(K * (size_t)N);
+        for (size_t k = 0; k < K; k++) memcpy(&sub[k * (size_t)N], llr + (size_t)failed[k] * N, (size_t)N * sizeof(double));
+        std::vector<uint32_t> t_bits(out->bits ? K * wpf : 0);
+        std::vector<uint8_t> t_dblk(out->dblk ? K * (size_t)N : 0), t_ok(K), t_pchk(out->pchk ? K * (size_t)M : 0);
+        std::vector<int32_t> t_it(K);
+        std::vector<double> t_post(out->posterior ? K * (size_t)N : 0);
+        dnaldpc_input in2 = in;
+        in2.data = sub.data();
+        in2.param = scales[r];
+        dnaldpc_output o2{};
+        o2.bits = out->bits ? t_bits.data() : nullptr;
+        o2.dblk = out->dblk ? t_dblk.data() : nullptr;
+        o2.iters = t_it.data();
+        o2.is_codeword = t_ok.data();
+        o2.posterior = out->posterior ? t_post.data() : nullptr;
+        o2.pchk = out->pchk ? t_pchk.data() : nullptr;
+        rc = dnaldpc_decode_batch(d, &in2, (int64_t)K, max_iter, &o2);
+        if (rc) return rc;
+        for (size_t k = 0; k < K; k++) {  // a frame keeps the result of its last round
+            const size_t f = (size_t)failed[k];
+            if (out->bits) memcpy(out->bits + f * wpf, &t_bits[k * wpf], wpf * 4);
+            if (out->dblk) memcpy(out->dblk + f * N, &t_dblk[k * (size_t)N], (size_t)N);
+            if (out->iters) out->iters[f] = t_it[k];
+            if (out->posterior) memcpy(out->posterior + f * N, &t_post[k * (size_t)N], (size_t)N * 8);
+            if (out->pchk) memcpy(out->pchk + f * M, &t_pchk[k * (size_t)M], (size_t)M);
+            ok[f] = t_ok[k];
+            if (rounds) rounds[f] = r;
+        }
+        total.frames += d->stats.frames; total.frame_iters += d->stats.frame_iters;
+        total.kernel_launches += d->stats.kernel_launches; total.waves += d->stats.waves;
+    }
+    if (out->is_codeword) memcpy(out->is_codeword, ok.data(), (size_t)F);
+    d->stats = total;
+    return DNALDPC_OK;
+}
+
 double dnaldpc_std_dev(double ebno_db, double rate) {  // channel.cpp:9-16
     const double enl = std::pow(10.0, ebno_db * 0.1);
     return 1 / std::sqrt(2 * rate * enl);

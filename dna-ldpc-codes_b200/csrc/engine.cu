@@ -175,6 +175,7 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
     a.data = in.data;
     a.frame_stride = in.frame_stride;
     a.param = in.param;
+    if (in.kind == DNALDPC_IN_LLR_F64 && in.param == 0.0) a.param = 1.0;
     a.table = d_table_;
     HarvestArgs h;
     h.bits = out.bits; h.dblk = out.dblk; h.posterior = out.posterior; h.wpf = (N_ + 31) / 32;
@@ -269,6 +270,7 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
                 if (rc) return rc;
                 syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)hgn[h]), kSynThreads, 0, hs[h]>>>(
                     d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, hg0[h], max_iter, round == 2,
+                    (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0,
                     round == 2 ? cnt : nullptr, (long long)F);
                 stats.kernel_launches++;
                 CK(cudaGetLastError());
@@ -359,7 +361,8 @@ int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const 
             h_exp_.resize((size_t)nf * N_);
             for (int64_t f = 0; f < nf; f++) {
                 const double *row = (const double *)(src + (size_t)f * stride);
-                for (int j = 0; j < N_; j++) h_exp_[(size_t)f * N_ + j] = std::exp(row[j]);
+                const double sc = in.param == 0.0 ? 1.0 : in.param;
+                for (int j = 0; j < N_; j++) h_exp_[(size_t)f * N_ + j] = std::exp(sc == 1.0 ? row[j] : sc * row[j]);
             }
             CK(cudaMemcpyAsync(s_in_, h_exp_.data(), (size_t)nf * packed, cudaMemcpyHostToDevice, st));
             w.kind = DNALDPC_IN_LR_F64;

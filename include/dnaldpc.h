@@ -86,13 +86,16 @@ void dnaldpc_decoder_destroy(dnaldpc_decoder *d);
 /* exp() is outside the bit-exact boundary (device exp != glibc exp != MSVC exp in the last ulp). With this flag a
  * HOST-pointer batch of kind LLR_F64 is exponentiated on the host with libm, like the reference does. */
 #define DNALDPC_FLAG_HOST_EXP 1
+/* Fixed-iteration BP = Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): no early exit, every frame runs exactly
+ * max_iter iterations; is_codeword reports the syndrome of the final decision. */
+#define DNALDPC_FLAG_FIXED_ITERS 2
 
 typedef struct dnaldpc_input {
     int32_t kind;        /* DNALDPC_IN_* */
     int32_t flags;       /* DNALDPC_FLAG_* */
     const void *data;    /* frame-major, frame f at data + f*frame_stride bytes */
     size_t frame_stride; /* 0 = tightly packed for the kind */
-    double param;        /* p | sigma | eps, per kind */
+    double param;        /* p | sigma | eps, per kind; LLR kinds: scale s, LR = exp(s*LLR) (0 = 1.0) */
     const double *table; /* VOTE_I8 only: optional LR table[256] indexed by (k+128); NULL = exp(k*L) by libm */
 } dnaldpc_input;
 
@@ -121,6 +124,16 @@ int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int
  * returns n in *iters; *is_codeword is written 0/1 (the reference leaves it untouched on failure). */
 int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_iter, char *dblk, char *pchk,
                            int *is_codeword, int *iters);
+
+/* Re-decoding sweep of the pipeline (ex_decoder/decoder.py:594-664): round r decodes, with LR = exp(scales[r]*LLR), the
+ * frames no earlier round turned into a codeword (round 0: all frames); the reference rescales the LLRs by
+ * ln((1-e2)/e2)/ln((1-e)/e) for e2 = e-0.0005, e-0.001, ... and launches ldpc.exe again per failed frame per round.
+ * Outputs hold each frame's result of its LAST round, rounds[f] (may be NULL) the index of that round. HOST buffers.
+ * Difference from the reference, on purpose: it calls a frame failed by comparing with the TRUE codeword
+ * (decoder.py:641-660), which a deployed decoder does not have; here a frame has failed when its syndrome is non-zero.
+ * flags: DNALDPC_FLAG_HOST_EXP for libm exp on the host (bit-exact with the reference's exe). */
+int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
+                           int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds);
 
 /* ---- likelihood-setup helpers (host) ----------------------------------------------------------- */
 double dnaldpc_std_dev(double ebno_db, double rate);                  /* getStd_dev, channel.cpp:9-16 */

@@ -218,6 +218,23 @@ int orc_bp_decode(const orc_code *c, const double *lratio, int max_iter, char *d
     return n;
 }
 
+/* dec.cpp:192-223 */
+int orc_bp_decode_fixed(const orc_code *c, const double *lratio, int max_iter, char *dblk, char *pchk, int *is_codeword) {
+    size_t E = (size_t)(c->E > 0 ? c->E : 1);
+    double *pr = (double *)malloc(sizeof(double) * E), *lr = (double *)malloc(sizeof(double) * E);
+    for (int e = 0; e < c->E; e++) { pr[e] = lratio[c->col_idx[e]]; lr[e] = 1; }
+    for (int j = 0; j < c->N; j++) dblk[j] = (lratio[j] < 1);
+    int n;
+    for (n = 0;; n++) {
+        if (n == max_iter) break;
+        bp_iter(c, lratio, dblk, pr, lr, NULL);
+    }
+    int w = orc_check(c, dblk, pchk);
+    if (is_codeword) *is_codeword = (w == 0);
+    free(pr); free(lr);
+    return n;
+}
+
 long orc_bp_decode_many(const orc_code *c, const double *lratio, int F, int max_iter, char *dblk,
                         int *iters, int *is_codeword) {
     long tot = 0;

@@ -48,6 +48,8 @@ int orc_check(const orc_code *c, const char *dblk, char *pchk);
  * msg_pr/msg_lr[E] (may be NULL: final e->pr / e->lr in CSR order). Returns n = iterations done. */
 int orc_bp_decode(const orc_code *c, const double *lratio, int max_iter, char *dblk, char *pchk,
                   int *is_codeword, double *posterior, double *msg_pr, double *msg_lr);
+/* Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): exactly max_iter iterations, syndrome checked once at the end. */
+int orc_bp_decode_fixed(const orc_code *c, const double *lratio, int max_iter, char *dblk, char *pchk, int *is_codeword);
 /* Same arithmetic in float (the optional fp32 mode; statistical parity only). */
 int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char *dblk, int *is_codeword);
 /* F frames, frame-major lratio[F][N], dblk[F][N]; returns total iterations. */

@@ -73,6 +73,15 @@ int ref_decode(const double *lratio, int maxit, char *dblk, char *pchk, int *is_
     return n;
 }
 
+/* Fixed-iteration variant, Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): no early exit. */
+int ref_decode_fixed(const double *lratio, int maxit, char *dblk, char *pchk, int *is_codeword) {
+    max_iter = maxit;
+    int flag = 0;
+    int n = Run_Belief_Propagation_Decoder_SAVE(H, (double *)lratio, dblk, pchk, &flag, (double **)0, 0, 0);
+    if (is_codeword) *is_codeword = flag;
+    return n;
+}
+
 /* check() alone (check.cpp:28-47). */
 int ref_check(const char *dblk, char *pchk) { return check(H, (char *)dblk, pchk); }
 

@@ -55,6 +55,7 @@ class Oracle:
             L.orc_check.argtypes = [C.POINTER(_Code), _cp, C.c_void_p]
             L.orc_bp_decode.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int),
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+            L.orc_bp_decode_fixed.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int)]
             L.orc_bp_decode_f32.argtypes = [C.POINTER(_Code), _fp, C.c_int, _cp, C.POINTER(C.c_int)]
             L.orc_bp_decode_many.restype = C.c_long
             L.orc_bp_decode_many.argtypes = [C.POINTER(_Code), _dp, C.c_int, C.c_int, _cp, _ip, _ip]
@@ -131,6 +132,14 @@ class Oracle:
                                      lr.ctypes.data if want_msgs else None)
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=post, pr=pr, lr=lr)
 
+    def decode_fixed(self, lratio, max_iter):
+        lratio = np.ascontiguousarray(lratio, dtype=np.float64)
+        dblk = np.zeros(self.N, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        ok = C.c_int(0)
+        n = self.lib().orc_bp_decode_fixed(self._c, lratio, max_iter, dblk, pchk.ctypes.data, C.byref(ok))
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk)
+
     def decode_f32(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float32)
         dblk = np.zeros(self.N, dtype=np.int8)
@@ -195,6 +204,7 @@ class RefLib:
             L.ref_check_regular.argtypes = [C.POINTER(C.c_int)] * 4
             L.ref_decode.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
             L.ref_check.argtypes = [_cp, _cp]
+            L.ref_decode_fixed.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int)]
             L.ref_decode_many.restype = C.c_long
             L.ref_decode_many.argtypes = [_dp, C.c_int, C.c_int, _cp, _ip, _ip]
             cls._lib = L
@@ -237,6 +247,14 @@ class RefLib:
                                  pr.ctypes.data if want_msgs else None,
                                  lr.ctypes.data if want_msgs else None)
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=post, pr=pr, lr=lr)
+
+    def decode_fixed(self, lratio, max_iter):
+        lratio = np.ascontiguousarray(lratio, dtype=np.float64)
+        dblk = np.zeros(self.N, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        ok = C.c_int(0)
+        n = self._lib.ref_decode_fixed(lratio, max_iter, dblk, pchk, C.byref(ok))
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk)
 
     def decode_many(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float64)

@@ -268,3 +268,39 @@ def test_multi_device_sharding(code18432, cws):
         assert np.array_equal(a[k], b[k])
     assert np.array_equal(a["post"].view(np.uint64), b["post"].view(np.uint64))
     one.close(); two.close()
+
+
+def test_fixed_iterations_and_redecode_sweep(code18432, orc18432, cws):
+    """fixed-iteration BP (Run_Belief_Propagation_Decoder_SAVE, dec.cpp:192-223) and the pipeline's
+    eps-sweep re-decoding (decoder.py:594-664) as one call."""
+    N = 18432
+    dec = ldpc.Decoder(code18432, wave_frames=64)
+    F = 40
+    lr = np.stack([_bsc_lr(cws[f], ol.bsc_flips(61, f, N, 0.006), 0.006) for f in range(F)])
+    r = dec.decode(ldpc.IN_LR_F64, lr, 7, flags=ldpc.FLAG_FIXED_ITERS, want=("bits", "iters", "ok", "pchk"))
+    assert (r["iters"] == 7).all()
+    for f in (0, 13, F - 1):
+        o = orc18432.decode_fixed(lr[f], 7)
+        assert r["ok"][f] == o["ok"] and np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"])
+    # re-decode sweep: vote-count LLRs computed with a too pessimistic eps fail at first, then decode once rescaled
+    rs = np.random.RandomState(8)
+    F = 24
+    eps = 0.02
+    reads = rs.poisson(2.2, (F, N))
+    k = reads - 2 * rs.binomial(reads, 0.04)
+    tx = cws[np.arange(F) % 272]
+    llr = np.where(tx == 0, k, -k) * np.log((1 - eps) / eps)
+    e2 = eps - 0.0005 * np.arange(0, 12)
+    scales = np.log((1 - e2) / e2) / np.log((1 - eps) / eps)       # decoder.py:611
+    res = dec.redecode_sweep(llr, 60, scales, flags=ldpc.FLAG_HOST_EXP)
+    # same thing by hand through the oracle: a frame moves to the next scale while its syndrome is non-zero
+    for f in range(0, F, 5):
+        for rnd, s in enumerate(scales):
+            lr_f = np.zeros(N)
+            ol.Oracle.lib().orc_lr_from_llr(np.ascontiguousarray(s * llr[f]), N, lr_f)
+            o = orc18432.decode(lr_f, 60, want_post=False)
+            if o["ok"] or rnd == len(scales) - 1:
+                break
+        assert res["rounds"][f] == rnd and res["ok"][f] == o["ok"] and res["iters"][f] == o["n"], f
+        assert np.array_equal(res["bits"][f], o["dblk"]), f
+    dec.close()

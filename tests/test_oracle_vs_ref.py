@@ -55,3 +55,15 @@ def test_check_matches(pair):
     wa, pa = ref.check(d)
     wb, pb = orc.check(d)
     assert wa == wb and np.array_equal(pa, pb)
+
+
+def test_fixed_iteration_variant(pair):
+    """Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): no early exit."""
+    ref, orc = pair
+    cws = ol.load_codewords()
+    N = ref.N
+    for f, eps, mi in [(3, 0.006, 9), (4, 0.0085, 5), (5, 0.004, 0)]:
+        lr = np.where((cws[f] ^ ol.bsc_flips(77, f, N, eps)) == 0, (1 - eps) / eps, eps / (1 - eps))
+        a, b = ref.decode_fixed(lr, mi), orc.decode_fixed(lr, mi)
+        assert a["n"] == b["n"] == mi and a["ok"] == b["ok"]
+        assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"])
