@@ -259,7 +259,7 @@ assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsign
 // `consider_new`: only slots admitted in this round are examined (the others were examined earlier this tick).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSynThreads = 256;
-constexpr int kSynSplit = 8;
+constexpr int kSynSplit = 64;  // CTAs per group; the last one to arrive applies the loop control
 
 __global__ void __launch_bounds__(kSynThreads)
 syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t *__restrict__ iters_out,
@@ -282,19 +282,23 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t
         return;
     }
     const uint32_t *dw = decw + (size_t)g * N;
-    const int rows_per = (M + kSynSplit - 1) / kSynSplit;
-    const int i_end = min(M, (int)(blockIdx.x + 1) * rows_per);
+    // 8 lanes per check: their index loads are one coalesced run and all gathers of a check are in flight at once
+    // (two dependent memory latencies per check instead of one per edge); XOR-folded over the 8 lanes with shuffles.
+    const int sub = threadIdx.x & 7;
+    const int rows_per_cta = kSynThreads / 8;
+    const int stride = gridDim.x * rows_per_cta;
     uint32_t acc = 0;
-    for (int i = blockIdx.x * rows_per + threadIdx.x; i < i_end; i += kSynThreads) {
+    for (int ib = blockIdx.x * rows_per_cta; ib < M; ib += stride) {  // warp-uniform trip count
+        const int i = ib + (threadIdx.x >> 3);
         uint32_t p = 0;
-        const int e1 = __ldg(row_ptr + i + 1);
-        int e = __ldg(row_ptr + i);
-        for (; e + 4 <= e1; e += 4) {  // 4 independent gathers in flight
-            const uint32_t a = __ldg(dw + __ldg(col_idx + e)), b = __ldg(dw + __ldg(col_idx + e + 1));
-            const uint32_t c = __ldg(dw + __ldg(col_idx + e + 2)), d = __ldg(dw + __ldg(col_idx + e + 3));
-            p ^= (a ^ b) ^ (c ^ d);
+        if (i < M) {
+            const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
+#pragma unroll 4
+            for (int e = e0 + sub; e < e1; e += 8) p ^= __ldg(dw + __ldg(col_idx + e));
         }
-        for (; e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
+        p ^= __shfl_xor_sync(0xffffffffu, p, 1);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 2);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 4);
         acc |= p;
     }
     acc = __reduce_or_sync(0xffffffffu, acc);
