@@ -133,7 +133,7 @@ def run_reference(args):
 def workload_config(args, frames):
     return {"workload": "configs[1]: n=18432/m=2048 code (decode_n18432_m2048_final.pchk), %d-frame batch per GPU, "
                         "codeword[f%%272] + synthetic BSC eps=%g, prprp max %d iterations" % (frames, args.eps, args.max_iter),
-            "frames_per_gpu": frames, "eps": args.eps, "max_iter": args.max_iter, "wave_frames": args.wave,
+            "frames_per_gpu": frames, "eps": args.eps, "max_iter": args.max_iter, "wave_frames": args.wave, "algorithm": args.alg,
             "l2": "inputs larger than L2: message working set %.1f GB per wave vs 126 MB L2" % (min(args.wave, frames) * E * 8 / 1e9)}
 
 
@@ -171,9 +171,14 @@ def run_ours(args):
     dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, frame0, F, args.eps, d_in.data_ptr(), stream)
     torch.cuda.synchronize()
 
+    flags = ldpc.FLAG_MINSUM if args.alg == "minsum" else 0
+
     def step_device():
-        dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), F, args.max_iter, param=args.eps, bits_ptr=d_bits.data_ptr(),
-                          iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=stream)
+        inp_d = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=flags, data=d_in.data_ptr(), frame_stride=0, param=args.eps, table=None)
+        out_d = ldpc.Output(bits=d_bits.data_ptr(), dblk=None, iters=d_it.data_ptr(), is_codeword=d_ok.data_ptr(), posterior=None, pchk=None)
+        rc = ldpc.lib().dnaldpc_decode_batch_device(dec._h, ldpc.C.byref(inp_d), F, args.max_iter, ldpc.C.byref(out_d), stream)
+        if rc:
+            raise RuntimeError(ldpc.lib().dnaldpc_last_error())
         return dec.stats()["kernel_launches"]
 
     def barrier():
@@ -207,7 +212,7 @@ def run_ours(args):
     h_it = torch.empty(F, dtype=torch.int32).pin_memory()
     h_ok = torch.empty(F, dtype=torch.uint8).pin_memory()
     C = ldpc.C
-    inp = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=0, data=h_in.data_ptr(), frame_stride=0, param=args.eps, table=None)
+    inp = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=flags, data=h_in.data_ptr(), frame_stride=0, param=args.eps, table=None)
     out = ldpc.Output(bits=h_bits.data_ptr(), dblk=None, iters=h_it.data_ptr(), is_codeword=h_ok.data_ptr(), posterior=None, pchk=None)
 
     def step_host():
@@ -238,8 +243,9 @@ def run_ours(args):
     peak, peak_src = peaks()
     pf = min(F, args.wave)
     dec.set_profiling(1)
-    dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), pf, min(args.max_iter, 24), param=args.eps, bits_ptr=d_bits.data_ptr(),
-                      iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=stream)
+    inp_p = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=flags, data=d_in.data_ptr(), frame_stride=0, param=args.eps, table=None)
+    out_p = ldpc.Output(bits=d_bits.data_ptr(), dblk=None, iters=d_it.data_ptr(), is_codeword=d_ok.data_ptr(), posterior=None, pchk=None)
+    ldpc.lib().dnaldpc_decode_batch_device(dec._h, C.byref(inp_p), pf, min(args.max_iter, 24), C.byref(out_p), stream)
     torch.cuda.synchronize()
     st = dec.stats()
     dec.set_profiling(0)
@@ -302,6 +308,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-frames-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--alg", default="bp", choices=["bp", "minsum"], help="bp = sum-product (the metric); minsum = floating min-sum (SURVEY 8f-4)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = bit-exact mode (the metric); f32 = optional fast mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

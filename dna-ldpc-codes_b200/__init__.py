@@ -17,6 +17,7 @@ PREC_F64, PREC_F32 = 0, 1
 IN_LR_F64, IN_LLR_F64, IN_BSC_BITS, IN_AWGN_F32, IN_AWGN_F64, IN_VOTE_I8 = range(6)
 FLAG_HOST_EXP = 1
 FLAG_FIXED_ITERS = 2
+FLAG_MINSUM = 4
 
 EXPORTS = [
     "dnaldpc_last_error", "dnaldpc_version", "dnaldpc_code_read_pchk", "dnaldpc_code_from_csr",

@@ -90,9 +90,45 @@ __device__ __forceinline__ void row_compute(T (&d)[DC], int deg, T *base, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Floating-point min-sum: Run_MSA_Decoder_INF, dec.cpp:1216-1250, in the LLR domain (positive = bit 0).
+//   check node (Check_Update_MSA_INF, dec.cpp:1398-1433): c2v_k = prod_{m != k} sign(v2c_m) * min_{m != k} |v2c_m|
+//   (sign(x) = +1 when x >= 0), 0 for a check of degree 1
+//   bit node (Variable_Update_MSA_INF, dec.cpp:1597-1618): v2c_k = LLR + sum_{m != k} c2v_m, added in ascending row
+//   decision (Decision_MSA_INF, dec.cpp:1659-1677): L = LLR + sum_m c2v_m; bit = !(L > 0)
+// Same slot layout and scheduler; `lratio` holds the channel LLR, `msg` holds v2c before / c2v after the check pass.
+// ------------------------------------------------------------------------------------------------
+enum Alg { ALG_BP = 0, ALG_MINSUM = 1 };
+
+template <typename T, int DC, bool EXACT>
+__device__ __forceinline__ void row_compute_minsum(T (&d)[DC], int deg, T *base) {
+    // smallest and second smallest magnitude (the first of equal magnitudes counts as "the" minimum, as in the
+    // reference's strict `mag_min > abs(..)` scan; equal values make the choice invisible), and the sign parity
+    T m1 = T(-1), m2 = T(-1);
+    int i1 = -1, neg = 0;
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < deg) {
+            const T a = fabs(d[k]);
+            neg ^= !(d[k] >= T(0));
+            if (i1 < 0 || m1 > a) { m2 = m1; m1 = a; i1 = k; }
+            else if (m2 < T(0) || m2 > a) m2 = a;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < deg) {
+            T mag = (k == i1) ? m2 : m1;
+            if (mag < T(0)) mag = T(0);                       // degree-1 check: no other edge (dec.cpp:1426-1427)
+            const int sneg = neg ^ (!(d[k] >= T(0)));         // parity of negative signs among the OTHER edges
+            st_stream(base + (size_t)k * kFG, (sneg ? T(-1) : T(1)) * mag);
+        }
+    }
+}
+
 // One (check i, slot f of group g): the DC loads go straight into the registers that then hold d_k, so all of them are
 // in flight at once. `mixed` (warp-uniform) = some lane of the warp starts a new frame and gathers lratio instead.
-template <typename T, int DC, bool EXACT>
+template <typename T, int DC, bool EXACT, int ALG>
 __device__ __forceinline__ void row_thread(T *__restrict__ msg, const T *__restrict__ lratio,
                                            const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
                                            int N, int E, int g, int i, int f, bool fresh, bool mixed) {
@@ -113,7 +149,8 @@ __device__ __forceinline__ void row_thread(T *__restrict__ msg, const T *__restr
                 d[k] = *src;  // default cache policy: a bit's lratio is re-read by every check it belongs to
             }
     }
-    row_compute<T, DC, EXACT>(d, deg, base, lr_lane, col_idx + e0, fresh);
+    if (ALG == ALG_MINSUM) row_compute_minsum<T, DC, EXACT>(d, deg, base);
+    else row_compute<T, DC, EXACT>(d, deg, base, lr_lane, col_idx + e0, fresh);
 }
 
 constexpr int kRowWarps = 4;
@@ -122,7 +159,7 @@ constexpr int kRowWarps = 4;
 // (Measured alternative, removed: slot-major kernels - a warp = 32 checks of ONE slot - for groups thinned out in the
 // drain tail of a batch. All 32 lanes then do useful arithmetic, but every lane touches its own 32 B sector and L1
 // wavefront; on B200 that was 10-20 % slower end to end than letting thin groups run through this kernel.)
-template <typename T, int DC, bool EXACT>
+template <typename T, int DC, bool EXACT, int ALG>
 __global__ void __launch_bounds__(kRowWarps * 32)
 row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
                 const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr,
@@ -135,7 +172,7 @@ row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_
     const uint32_t act = actw[g];
     if (!((act >> lane) & 1u)) return;            // finished / empty slots keep their messages untouched
     const uint32_t fw = freshw[g];                // warp-uniform
-    row_thread<T, DC, EXACT>(msg, lratio, row_ptr, col_idx, N, E, g, i, lane, (fw >> lane) & 1u, fw != 0);
+    row_thread<T, DC, EXACT, ALG>(msg, lratio, row_ptr, col_idx, N, E, g, i, lane, (fw >> lane) & 1u, fw != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -146,7 +183,7 @@ row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_
 // ------------------------------------------------------------------------------------------------
 constexpr int kColWarps = 8;
 
-template <typename T, int DV, bool EXACT>
+template <typename T, int DV, bool EXACT, int ALG>
 __device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restrict__ lratio, T *__restrict__ post,
                                            const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
                                            int N, int E, int g, int j, int f, bool on) {
@@ -160,6 +197,25 @@ __device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restr
 #pragma unroll
     for (int k = 0; k < DV; k++) lr[k] = (on && (EXACT || k < deg)) ? ld_stream(gmsg + (size_t)eid[k] * kFG) : T(1);
     T P = on ? __ldg(lratio + ((size_t)g * N + j) * kFG + f) : T(1);
+    if (ALG == ALG_MINSUM) {  // lr[] = c2v LLRs, P = channel LLR; sums in ascending row order, own edge skipped
+        const T llr = P;
+#pragma unroll
+        for (int k = 0; k < DV; k++) {
+            if (EXACT || k < deg) {
+                T sum = llr;
+#pragma unroll
+                for (int m = 0; m < DV; m++)
+                    if (m != k && (EXACT || m < deg)) sum = sum + lr[m];
+                if (on) st_stream(gmsg + (size_t)eid[k] * kFG, sum);
+            }
+        }
+        T tot = llr;
+#pragma unroll
+        for (int m = 0; m < DV; m++)
+            if (EXACT || m < deg) tot = tot + lr[m];
+        if (post != nullptr && on) post[((size_t)g * N + j) * kFG + f] = tot;
+        return !(tot > T(0));
+    }
     T p[DV];
 #pragma unroll
     for (int k = 0; k < DV; k++) {
@@ -181,7 +237,7 @@ __device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restr
     return P <= T(1);
 }
 
-template <typename T, int DV, bool EXACT>
+template <typename T, int DV, bool EXACT, int ALG>
 __global__ void __launch_bounds__(kColWarps * 32)
 col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__restrict__ decw,
                 const uint32_t *__restrict__ actw, T *__restrict__ post, const int32_t *__restrict__ col_ptr,
@@ -194,7 +250,7 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
     const int jbeg = (blockIdx.x * kColWarps + warp) * cols_per_warp;
     const int jend = min(jbeg + cols_per_warp, N);
     for (int j = jbeg; j < jend; j++) {
-        const bool bit = col_thread<T, DV, EXACT>(msg, lratio, post, col_ptr, col_edge, N, E, g, j, lane, on);
+        const bool bit = col_thread<T, DV, EXACT, ALG>(msg, lratio, post, col_ptr, col_edge, N, E, g, j, lane, on);
         const uint32_t w = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) {
             uint32_t *dst = decw + (size_t)g * N + j;
@@ -385,9 +441,20 @@ template <int KIND> __device__ __forceinline__ double load_lr(const SetupArgs &a
     return a.table[(int)((const int8_t *)row)[j] + 128];
 }
 
+// channel LLR = ln(p0/p1) of a bit, for the LLR-domain decoder (min-sum). Tables hold LLRs here.
+template <int KIND> __device__ __forceinline__ double load_llr(const SetupArgs &a, long long fr, int j) {
+    const char *row = (const char *)a.data + (size_t)fr * a.frame_stride;
+    if (KIND == IN_LR_F64) return log(((const double *)row)[j]);
+    if (KIND == IN_LLR_F64) return a.param == 1.0 ? ((const double *)row)[j] : a.param * ((const double *)row)[j];
+    if (KIND == IN_BSC_BITS) return a.table[(((const uint32_t *)row)[j >> 5] >> (j & 31)) & 1u];
+    if (KIND == IN_AWGN_F32) return 2.0 * (double)((const float *)row)[j] / (a.param * a.param);   // channel.cpp:32
+    if (KIND == IN_AWGN_F64) return 2.0 * ((const double *)row)[j] / (a.param * a.param);
+    return a.table[(int)((const int8_t *)row)[j] + 128];
+}
+
 constexpr int kHsTiles = 16;  // 32-bit tiles per CTA: keeps the (usually idle) launch down to a few thousand CTAs
 
-template <typename T, int KIND>
+template <typename T, int KIND, int ALG>
 __global__ void __launch_bounds__(256)
 harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ lratio, const T *__restrict__ post,
                      uint32_t *__restrict__ decw, int N, int g0) {
@@ -441,14 +508,15 @@ harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ 
             for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit of the tile
                 const int j = j0 + tx;
                 double v = 1.0;
-                if (((nf >> r) & 1u) && j < N) v = load_lr<KIND>(a, s_new[r], j);
+                if (((nf >> r) & 1u) && j < N) v = ALG == ALG_MINSUM ? load_llr<KIND>(a, s_new[r], j) : load_lr<KIND>(a, s_new[r], j);
                 tile[r][tx] = v;
             }
             __syncthreads();
             for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
                 const int j = j0 + r;
-                const T v = clamp_lr((T)tile[tx][r]);
-                const uint32_t w = __ballot_sync(0xffffffffu, v < T(1));
+                const T v = ALG == ALG_MINSUM ? (T)tile[tx][r] : clamp_lr((T)tile[tx][r]);
+                // initial decision: BP lratio < 1 (dec.cpp:626); min-sum !(LLR > 0) (Init_MSA_INF, dec.cpp:1311-1312)
+                const uint32_t w = __ballot_sync(0xffffffffu, ALG == ALG_MINSUM ? !(v > T(0)) : (v < T(1)));
                 if (j < N) {
                     if ((nf >> tx) & 1u) lratio[((size_t)g * N + j) * kFG + tx] = v;
                     if (tx == 0) {

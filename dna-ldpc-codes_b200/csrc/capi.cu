@@ -242,7 +242,7 @@ int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int
     std::vector<uint8_t> ok((size_t)F, 0);
     dnaldpc_input in{};
     in.kind = DNALDPC_IN_LLR_F64;
-    in.flags = flags & (DNALDPC_FLAG_HOST_EXP | DNALDPC_FLAG_FIXED_ITERS);
+    in.flags = flags & (DNALDPC_FLAG_HOST_EXP | DNALDPC_FLAG_FIXED_ITERS | DNALDPC_FLAG_MINSUM);
     in.data = llr;
     in.param = scales[0];
     dnaldpc_output o = *out;

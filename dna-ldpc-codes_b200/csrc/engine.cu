@@ -137,7 +137,11 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     fill_sched(s);
     const long long items = (long long)G * M_;
     const unsigned grid = (unsigned)((items + kRowWarps - 1) / kRowWarps);
-#define ROW(DC, EX) row_pass_kernel<T, DC, EX><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G)
+#define ROW(DC, EX)                                                                                                                       \
+    do {                                                                                                                                  \
+        if (minsum_) row_pass_kernel<T, DC, EX, ALG_MINSUM><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G); \
+        else row_pass_kernel<T, DC, EX, ALG_BP><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);         \
+    } while (0)
     if (reg_rows_ && max_row_deg_ == 72) ROW(72, true);
     else if (max_row_deg_ <= 8) ROW(8, false);
     else if (max_row_deg_ <= 32) ROW(32, false);
@@ -157,7 +161,11 @@ template <typename T> int Engine::launch_col(int g0, int G, bool want_post, cuda
     fill_sched(s);
     const int cpw = 8;  // columns per warp
     dim3 grid((unsigned)((N_ + kColWarps * cpw - 1) / (kColWarps * cpw)), (unsigned)G);
-#define COL(DV, EX) col_pass_kernel<T, DV, EX><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw)
+#define COL(DV, EX)                                                                                                                      \
+    do {                                                                                                                                 \
+        if (minsum_) col_pass_kernel<T, DV, EX, ALG_MINSUM><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw); \
+        else col_pass_kernel<T, DV, EX, ALG_BP><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw);         \
+    } while (0)
     if (reg_cols_ && max_col_deg_ == 8) COL(8, true);
     else if (reg_cols_ && max_col_deg_ == 3) COL(3, true);
     else if (max_col_deg_ <= 4) COL(4, false);
@@ -189,7 +197,11 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
     dim3 grid((unsigned)(((N_ + 31) / 32 + kHsTiles - 1) / kHsTiles), (unsigned)G);
     T *lr = (T *)d_lratio_;
     const T *post = (const T *)d_post_;
-#define HS(K) harvest_setup_kernel<T, K><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0)
+#define HS(K)                                                                                                   \
+    do {                                                                                                        \
+        if (minsum_) harvest_setup_kernel<T, K, ALG_MINSUM><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0); \
+        else harvest_setup_kernel<T, K, ALG_BP><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0);         \
+    } while (0)
     switch (in.kind) {
         case DNALDPC_IN_LR_F64: HS(IN_LR_F64); break;
         case DNALDPC_IN_LLR_F64: HS(IN_LLR_F64); break;
@@ -222,12 +234,19 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
         if (!out.iters) out.iters = d_iters_;
         if (!out.is_codeword) out.is_codeword = d_ok_;
     }
+    minsum_ = (in.flags & DNALDPC_FLAG_MINSUM) != 0;
     if (in.kind == DNALDPC_IN_BSC_BITS || in.kind == DNALDPC_IN_VOTE_I8) {
         double tab[256];
         int cnt = 256;
-        if (in.kind == DNALDPC_IN_BSC_BITS) { dnaldpc_bsc_table(in.param, tab); cnt = 2; }
-        else if (in.table) memcpy(tab, in.table, sizeof(tab));
-        else dnaldpc_vote_table(in.param, tab);
+        if (in.kind == DNALDPC_IN_BSC_BITS) {
+            dnaldpc_bsc_table(in.param, tab);
+            cnt = 2;
+            if (minsum_) { tab[0] = std::log(tab[0]); tab[1] = std::log(tab[1]); }  // received_LLR = log(received_LR), channel.cpp:78,83
+        } else if (in.table) memcpy(tab, in.table, sizeof(tab));  // caller's table: ratios for BP, LLRs for min-sum
+        else if (minsum_) {
+            const double L = std::log((1 - in.param) / in.param);
+            for (int k = -128; k < 128; k++) tab[k + 128] = k * L;                   // decoder.py:314
+        } else dnaldpc_vote_table(in.param, tab);
         // pageable source: copied to a driver staging buffer before the call returns
         CK(cudaMemcpyAsync(d_table_, tab, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
     }
@@ -345,7 +364,7 @@ int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const 
     const size_t packed = in_elem_stride(in.kind, N_);
     if (packed == 0) return fail("unknown input kind", DNALDPC_ERR_ARG);
     const size_t wpf = (size_t)(N_ + 31) / 32;
-    const bool host_exp = in.kind == DNALDPC_IN_LLR_F64 && (in.flags & DNALDPC_FLAG_HOST_EXP);
+    const bool host_exp = in.kind == DNALDPC_IN_LLR_F64 && (in.flags & DNALDPC_FLAG_HOST_EXP) && !(in.flags & DNALDPC_FLAG_MINSUM);
     // Host batches are staged to the device in chunks; inside a chunk frames flow continuously through the slots.
     const int64_t budget = (int64_t)3 << 30;  // ~3 GB of staged input + outputs per chunk
     const size_t per_frame = packed + (out.bits ? wpf * 4 : 0) + (out.dblk ? (size_t)N_ : 0) + (out.posterior ? (size_t)N_ * 8 : 0) +

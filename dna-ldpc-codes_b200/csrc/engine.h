@@ -49,6 +49,7 @@ class Engine {
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
+    bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
     // H edge tables (device)
     int32_t *d_row_ptr_ = nullptr, *d_col_idx_ = nullptr, *d_col_ptr_ = nullptr, *d_col_edge_ = nullptr;

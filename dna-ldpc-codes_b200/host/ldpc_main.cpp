@@ -6,7 +6,7 @@
 // Reads <codeword_base>.txt (true codeword), <soft_base>.txt (LLR = ln(p0/p1)) and <pchk_base>.pchk from the CWD,
 // writes dec_<codeword_base>.txt, result_(...).txt and the same stdout summary as the reference
 // (Set_Code :552-556, Run_Simulation :916-927, Print_One_Result :1170-1182, Print_All_Result :1048-1123).
-// Only decoder_type 0 (BP) without punctuation / shortening / targeting is in scope; anything else is rejected.
+// Decoder types 0 (BP) and 20-22 (floating min-sum) without punctuation / shortening / targeting; anything else is rejected.
 //
 // Extensions (after the positional block, none of them changes the reference behaviour when absent):
 //   --device N        CUDA device ordinal (default 0)
@@ -90,8 +90,11 @@ void check(int rc) {
 
 int main(int argc, char **argv) {
     Args a = parse(argc, argv);
-    if (a.decoder_type != 0) {
-        fprintf(stderr, "ldpc: decoder type %d is not supported by this build (only 0 = belief propagation)\n", a.decoder_type);
+    // 0 = belief propagation; 20/21/22 = min-sum: with g_precision == 0 (the CLI cannot set it) all three reach the
+    // floating-point Run_MSA_Decoder_INF (DNA_main.cpp:1588-1594)
+    const bool minsum = a.decoder_type == 20 || a.decoder_type == 21 || a.decoder_type == 22;
+    if (a.decoder_type != 0 && !minsum) {
+        fprintf(stderr, "ldpc: decoder type %d is not supported by this build (0 = belief propagation, 20-22 = floating min-sum)\n", a.decoder_type);
         return 1;
     }
     if (a.punctuation || a.shortening || a.targeting) {
@@ -170,8 +173,9 @@ int main(int argc, char **argv) {
     std::vector<unsigned char> dblk(F * (size_t)N), okflag(F);
     std::vector<int32_t> iters(F);
     dnaldpc_input in{};
-    in.kind = DNALDPC_IN_LR_F64;
-    in.data = lr.data();
+    in.kind = minsum ? DNALDPC_IN_LLR_F64 : DNALDPC_IN_LR_F64;   // min-sum works on the LLRs themselves
+    in.flags = minsum ? DNALDPC_FLAG_MINSUM : 0;
+    in.data = minsum ? llr.data() : lr.data();
     dnaldpc_output out{};
     out.dblk = dblk.data();
     out.iters = iters.data();

@@ -89,6 +89,11 @@ void dnaldpc_decoder_destroy(dnaldpc_decoder *d);
 /* Fixed-iteration BP = Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): no early exit, every frame runs exactly
  * max_iter iterations; is_codeword reports the syndrome of the final decision. */
 #define DNALDPC_FLAG_FIXED_ITERS 2
+/* Floating-point min-sum instead of sum-product = Run_MSA_Decoder_INF (dec.cpp:1216-1250; decoder types 20-22 of the
+ * reference CLI, DNA_main.cpp:1588-1594). LLR domain: `posterior` receives L = LLR + sum of check messages
+ * (Decision_MSA_INF, dec.cpp:1659-1677); a user table for VOTE_I8 must hold LLRs. LR_F64 inputs are converted with the
+ * device log() and AWGN / LLR / BSC / vote-count inputs are exact. */
+#define DNALDPC_FLAG_MINSUM 4
 
 typedef struct dnaldpc_input {
     int32_t kind;        /* DNALDPC_IN_* */

@@ -248,6 +248,53 @@ long orc_bp_decode_many(const orc_code *c, const double *lratio, int F, int max_
     return tot;
 }
 
+/* ---------- floating-point min-sum (LLR domain) ------------------------------------------------ */
+
+int orc_minsum_decode(const orc_code *c, const double *llr, int max_iter, char *dblk, char *pchk, int *is_codeword, double *L) {
+    size_t E = (size_t)(c->E > 0 ? c->E : 1);
+    double *v2c = (double *)malloc(sizeof(double) * E), *c2v = (double *)calloc(E, sizeof(double));
+    /* Init_MSA_INF dec.cpp:1300-1314 */
+    for (int e = 0; e < c->E; e++) v2c[e] = llr[c->col_idx[e]];
+    for (int j = 0; j < c->N; j++) dblk[j] = (llr[j] > 0) ? 0 : 1;
+    int n, w;
+    for (n = 0;; n++) {
+        w = orc_check(c, dblk, pchk);
+        if (n == max_iter) break;
+        if (w == 0) break;
+        /* Check_Update_MSA_INF dec.cpp:1398-1433 */
+        for (int i = 0; i < c->M; i++)
+            for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) {
+                double mag_min = -1;
+                int sign = 1;
+                for (int g = c->row_ptr[i]; g < c->row_ptr[i + 1]; g++) {
+                    if (g == e) continue;
+                    if (mag_min == -1 || mag_min > fabs(v2c[g])) mag_min = fabs(v2c[g]);
+                    if (v2c[g] >= 0) sign *= 1; else sign *= -1;
+                }
+                if (mag_min < 0) mag_min = 0;
+                c2v[e] = sign * mag_min;
+            }
+        /* Variable_Update_MSA_INF dec.cpp:1597-1618 */
+        for (int j = 0; j < c->N; j++)
+            for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) {
+                double sum = llr[j];
+                for (int m = c->col_ptr[j]; m < c->col_ptr[j + 1]; m++)
+                    if (m != k) sum += c2v[c->col_edge[m]];
+                v2c[c->col_edge[k]] = sum;
+            }
+        /* Decision_MSA_INF dec.cpp:1659-1677 */
+        for (int j = 0; j < c->N; j++) {
+            double sum = llr[j];
+            for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) sum += c2v[c->col_edge[k]];
+            if (L) L[j] = sum;
+            dblk[j] = (sum > 0) ? 0 : 1;
+        }
+    }
+    if (is_codeword) *is_codeword = (w == 0);
+    free(v2c); free(c2v);
+    return n;
+}
+
 /* ---------- belief propagation, fp32 (statistical parity only) --------------------------- */
 
 int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char *dblk, int *is_codeword) {

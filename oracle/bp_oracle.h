@@ -50,6 +50,10 @@ int orc_bp_decode(const orc_code *c, const double *lratio, int max_iter, char *d
                   int *is_codeword, double *posterior, double *msg_pr, double *msg_lr);
 /* Run_Belief_Propagation_Decoder_SAVE (dec.cpp:192-223): exactly max_iter iterations, syndrome checked once at the end. */
 int orc_bp_decode_fixed(const orc_code *c, const double *lratio, int max_iter, char *dblk, char *pchk, int *is_codeword);
+/* Floating-point min-sum, Run_MSA_Decoder_INF (dec.cpp:1216-1250) with Init_MSA_INF (1300-1314), Check_Update_MSA_INF
+ * (1398-1433), Variable_Update_MSA_INF (1597-1618), Decision_MSA_INF (1659-1677). llr[N] = ln(p0/p1); L (may be NULL)
+ * receives the posterior LLR of the last decision (untouched when n == 0, like the reference's g_L). */
+int orc_minsum_decode(const orc_code *c, const double *llr, int max_iter, char *dblk, char *pchk, int *is_codeword, double *L);
 /* Same arithmetic in float (the optional fp32 mode; statistical parity only). */
 int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char *dblk, int *is_codeword);
 /* F frames, frame-major lratio[F][N], dblk[F][N]; returns total iterations. */

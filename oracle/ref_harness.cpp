@@ -82,6 +82,15 @@ int ref_decode_fixed(const double *lratio, int maxit, char *dblk, char *pchk, in
     return n;
 }
 
+/* Floating-point min-sum, Run_MSA_Decoder_INF (dec.cpp:1216-1250). L (N doubles) = posterior LLR of the last decision. */
+int ref_decode_minsum(const double *llr, int maxit, char *dblk, char *pchk, int *is_codeword, double *L) {
+    max_iter = maxit;
+    int flag = 0;
+    int n = Run_MSA_Decoder_INF(H, (double *)llr, L, dblk, pchk, &flag);
+    if (is_codeword) *is_codeword = flag;
+    return n;
+}
+
 /* check() alone (check.cpp:28-47). */
 int ref_check(const char *dblk, char *pchk) { return check(H, (char *)dblk, pchk); }
 

@@ -56,6 +56,7 @@ class Oracle:
             L.orc_bp_decode.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int),
                                         C.c_void_p, C.c_void_p, C.c_void_p]
             L.orc_bp_decode_fixed.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int)]
+            L.orc_minsum_decode.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
             L.orc_bp_decode_f32.argtypes = [C.POINTER(_Code), _fp, C.c_int, _cp, C.POINTER(C.c_int)]
             L.orc_bp_decode_many.restype = C.c_long
             L.orc_bp_decode_many.argtypes = [C.POINTER(_Code), _dp, C.c_int, C.c_int, _cp, _ip, _ip]
@@ -140,6 +141,15 @@ class Oracle:
         n = self.lib().orc_bp_decode_fixed(self._c, lratio, max_iter, dblk, pchk.ctypes.data, C.byref(ok))
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk)
 
+    def decode_minsum(self, llr, max_iter):
+        llr = np.ascontiguousarray(llr, dtype=np.float64)
+        dblk = np.zeros(self.N, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        L = np.array(llr, dtype=np.float64)  # n == 0 leaves it untouched; we define it as the channel LLR then
+        ok = C.c_int(0)
+        n = self.lib().orc_minsum_decode(self._c, llr, max_iter, dblk, pchk.ctypes.data, C.byref(ok), L.ctypes.data)
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=L)
+
     def decode_f32(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float32)
         dblk = np.zeros(self.N, dtype=np.int8)
@@ -205,6 +215,7 @@ class RefLib:
             L.ref_decode.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
             L.ref_check.argtypes = [_cp, _cp]
             L.ref_decode_fixed.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int)]
+            L.ref_decode_minsum.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int), _dp]
             L.ref_decode_many.restype = C.c_long
             L.ref_decode_many.argtypes = [_dp, C.c_int, C.c_int, _cp, _ip, _ip]
             cls._lib = L
@@ -255,6 +266,15 @@ class RefLib:
         ok = C.c_int(0)
         n = self._lib.ref_decode_fixed(lratio, max_iter, dblk, pchk, C.byref(ok))
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk)
+
+    def decode_minsum(self, llr, max_iter):
+        llr = np.ascontiguousarray(llr, dtype=np.float64)
+        dblk = np.zeros(self.N, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        L = np.array(llr, dtype=np.float64)
+        ok = C.c_int(0)
+        n = self._lib.ref_decode_minsum(llr, max_iter, dblk, pchk, C.byref(ok), L)
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=L)
 
     def decode_many(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float64)

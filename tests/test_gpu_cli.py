@@ -77,3 +77,29 @@ def test_cli_errors_and_batch_list(tmp_path):
         got = np.array(open(os.path.join(tmp, "dec_%s.txt" % cwname)).read().split(), dtype=np.int8)
         assert np.array_equal(got, cws[f])
     assert b"frame_num              : 5" in r.stdout and b"bit_err                : 0" in r.stdout
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ldpc_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ldpc_ref not built")
+@pytest.mark.parametrize("dectype", ["0", "20"])
+def test_cli_side_by_side_with_reference_binary(tmp_path, dectype):
+    """Our CLI and the unmodified reference CLI (prebuilt oracle/_ref/ldpc_ref) on the same files: BP (type 0) and
+    floating min-sum (type 20, Run_MSA_Decoder_INF)."""
+    cws = ol.load_codewords()
+    outs = {}
+    for who, exe in (("ours", LDPC), ("ref", REF_CLI)):
+        d = str(tmp_path / who)
+        os.makedirs(d)
+        shutil.copyfile(ol.PCHK_18432, os.path.join(d, "H.pchk"))
+        eps = 0.005
+        llr = np.where((cws[3] ^ ol.bsc_flips(17, 3, 18432, eps)) == 0, 1.0, -1.0) * np.log((1 - eps) / eps) * np.linspace(0.7, 1.3, 18432)
+        cwname, softname = _write_inputs(d, 3, llr, cws)
+        r = subprocess.run([exe, "0", dectype, "0", "7", "60", "1", cwname, softname, "H", "0", "0", "0", "0"], cwd=d, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        res = [f for f in os.listdir(d) if f.startswith("result_")]
+        assert len(res) == 1
+        outs[who] = (r.stdout, open(os.path.join(d, "dec_%s.txt" % cwname), "rb").read(), res[0],
+                     _strip_times(open(os.path.join(d, res[0])).read()))
+    assert outs["ours"] == outs["ref"]

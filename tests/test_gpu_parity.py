@@ -304,3 +304,47 @@ def test_fixed_iterations_and_redecode_sweep(code18432, orc18432, cws):
         assert res["rounds"][f] == rnd and res["ok"][f] == o["ok"] and res["iters"][f] == o["n"], f
         assert np.array_equal(res["bits"][f], o["dblk"]), f
     dec.close()
+
+
+def test_minsum_decoder(code18432, orc18432, cws):
+    """floating-point min-sum (Run_MSA_Decoder_INF, dec.cpp:1216-1250): decisions, n, syndromes and the
+    posterior LLRs bit-exact against the oracle, for every input kind whose LLR is exact on the device."""
+    N = 18432
+    rs = np.random.RandomState(14)
+    dec = ldpc.Decoder(code18432, wave_frames=64)
+    F = 50
+    eps_of = [0.0005, 0.0015, 0.0025, 0.003]   # min-sum decodes this (8,72) code only below eps ~ 0.003
+    recv = np.stack([cws[f] ^ ol.bsc_flips(90, f, N, eps_of[f % 4]) for f in range(F)]).astype(np.uint8)
+    llr = np.stack([np.where(recv[f] == 0, 1.0, -1.0) * np.log((1 - eps_of[f % 4]) / eps_of[f % 4]) for f in range(F)])
+    llr[7] = np.where(cws[7] == 0, 1.0, -1.0) * rs.poisson(3.0, N) * np.log(49.0)   # exact zeros and many ties
+    r = dec.decode(ldpc.IN_LLR_F64, llr, 40, flags=ldpc.FLAG_MINSUM, want=("bits", "iters", "ok", "post", "pchk"))
+    for f in range(0, F, 3):
+        o = orc18432.decode_minsum(llr[f], 40)
+        assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], f
+        assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), f
+        assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
+    assert len(set(r["iters"].tolist())) >= 3
+    # BSC bits: LLR table = log of the two ratios (channel.cpp:78,83)
+    p = 0.002
+    recv8 = np.stack([cws[f] ^ ol.bsc_flips(91, f, N, p) for f in range(8)]).astype(np.uint8)
+    packed = np.packbits(recv8, axis=1, bitorder="little").view(np.uint32)
+    a = dec.decode(ldpc.IN_BSC_BITS, packed, 40, param=p, flags=ldpc.FLAG_MINSUM)
+    t = np.log(ldpc.bsc_table(p))
+    for f in (0, 5):
+        o = orc18432.decode_minsum(t[recv8[f]], 40)
+        assert a["iters"][f] == o["n"] and np.array_equal(a["bits"][f], o["dblk"])
+    # AWGN: LLR = 2y/sigma^2 is exact on the device (no exp in the LLR domain)
+    sigma = ldpc.std_dev(5.0, 1 - 2048 / 18432)
+    y = np.where(cws[:6] == 0, 1.0, -1.0) + sigma * rs.randn(6, N)
+    a = dec.decode(ldpc.IN_AWGN_F64, y, 60, param=sigma, flags=ldpc.FLAG_MINSUM, want=("bits", "iters", "ok", "post"))
+    for f in range(6):
+        o = orc18432.decode_minsum(2.0 * y[f] / (sigma * sigma), 60)
+        assert a["iters"][f] == o["n"] and a["ok"][f] == o["ok"] and np.array_equal(a["bits"][f], o["dblk"])
+        assert np.array_equal(a["post"][f].view(np.uint64), o["post"].view(np.uint64))
+    # vote counts: LLR = k * ln((1-eps)/eps)
+    k = rs.poisson(3.5, (4, N)) - 2 * rs.binomial(4, 0.02, (4, N))
+    k = np.where(cws[:4] == 0, k, -k).astype(np.int8)
+    a = dec.decode(ldpc.IN_VOTE_I8, k, 60, param=0.02, flags=ldpc.FLAG_MINSUM)
+    o = orc18432.decode_minsum(k[2].astype(np.float64) * np.log((1 - 0.02) / 0.02), 60)
+    assert a["iters"][2] == o["n"] and np.array_equal(a["bits"][2], o["dblk"])
+    dec.close()

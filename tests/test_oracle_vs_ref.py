@@ -67,3 +67,23 @@ def test_fixed_iteration_variant(pair):
         a, b = ref.decode_fixed(lr, mi), orc.decode_fixed(lr, mi)
         assert a["n"] == b["n"] == mi and a["ok"] == b["ok"]
         assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"])
+
+
+def test_minsum_variant(pair):
+    """Run_MSA_Decoder_INF (dec.cpp:1216-1250): floating-point min-sum in the LLR domain."""
+    ref, orc = pair
+    cws = ol.load_codewords()
+    N = ref.N
+    rs = np.random.RandomState(12)
+    sigma = 1 / np.sqrt(2 * (1 - 2048 / 18432) * 10 ** 0.5)
+    cases = []
+    for f, eps, mi in [(3, 0.004, 50), (4, 0.006, 30), (5, 0.004, 0), (6, 0.02, 3)]:
+        cases.append((np.where((cws[f] ^ ol.bsc_flips(78, f, N, eps)) == 0, 1.0, -1.0) * np.log((1 - eps) / eps), mi))
+    cases.append((2 * (np.where(cws[7] == 0, 1.0, -1.0) + sigma * rs.randn(N)) / sigma ** 2, 40))
+    llr = np.where(cws[8] == 0, 1.0, -1.0) * rs.poisson(3.0, N) * np.log(49.0)   # many exact zeros and ties
+    cases.append((llr, 25))
+    for llr, mi in cases:
+        a, b = ref.decode_minsum(llr, mi), orc.decode_minsum(llr, mi)
+        assert a["n"] == b["n"] and a["ok"] == b["ok"]
+        assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"])
+        assert np.array_equal(a["post"].view(np.uint64), b["post"].view(np.uint64))
