@@ -175,6 +175,114 @@ row_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_
     row_thread<T, DC, EXACT, ALG>(msg, lratio, row_ptr, col_idx, N, E, g, i, lane, (fw >> lane) & 1u, fw != 0);
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier helpers --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on the mbarrier as transferred bytes
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Check pass with the check's 72 x 32 messages staged in shared memory (regular codes): ONE 18 KB cp.async.bulk per
+// warp lands the contiguous run in the warp's tile, the factors d_k overwrite the tile in place, and only the 9
+// check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
+// <= 168 registers: 12 warps (3 CTAs, 3 x 73.8 KB of shared memory) per SM instead of 8, i.e. 50 % more bytes in flight.
+// Slots that start a frame then overwrite their column with gathered channel ratios; groups with idle slots (drain
+// tail: finished lanes must not be loaded or stored) fill the tile lane by lane instead.
+template <typename T, int DC>
+__global__ void __launch_bounds__(kRowWarps * 32, 3)
+row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
+                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
+                     int g0, int G) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRowWarps * DC * kFG * sizeof(T)) + warp;
+    const long long item = (long long)blockIdx.x * kRowWarps + warp;
+    if (item >= (long long)G * M) return;
+    const int gl = (int)(item / M), i = (int)(item - (long long)gl * M);
+    const int g = g0 + gl;
+    const uint32_t act = actw[g];
+    if (act == 0) return;
+    const uint32_t fw = freshw[g];
+    const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
+    const int e0 = i * DC;
+    T *base = msg + ((size_t)g * E + e0) * kFG + lane;
+    T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
+    const T *lr_lane = lratio + (size_t)g * N * kFG + lane;
+    if (act == 0xffffffffu) {  // warp-uniform: every slot of the group is busy -> one bulk copy for the whole tile
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(bar, (uint32_t)(DC * kFG * sizeof(T)));
+            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(DC * kFG * sizeof(T)), bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        if (fresh) {  // slots that start a frame replace their column by the channel ratios of the check's bits
+#pragma unroll 24
+            for (int k = 0; k < DC; k++) col[k * kFG] = lr_lane[(size_t)__ldg(col_idx + e0 + k) * kFG];
+        }
+    } else {  // drain tail: finished / empty lanes must not be loaded or stored
+        if (!on) return;
+#pragma unroll 24
+        for (int k = 0; k < DC; k++)
+            col[k * kFG] = fresh ? lr_lane[(size_t)__ldg(col_idx + e0 + k) * kFG] : ld_stream(base + (size_t)k * kFG);
+    }
+    // pass 1, descending: d_k in place, backward products check-pointed every 8 edges
+    constexpr int NB = (DC + 7) / 8;
+    T ck[NB];
+    T B = T(1);
+    bool bad = false;
+#pragma unroll
+    for (int k = DC - 1; k >= 0; k--) {
+        const T dk = check_factor(col[k * kFG], bad);
+        col[k * kFG] = dk;
+        if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
+        B = mul_rn(B, dk);
+    }
+    if (bad) {  // invalid likelihood ratios: nothing stored to msg yet, redo with full IEEE divisions
+        row_slow_path<T>(base, lr_lane, col_idx + e0, DC, fresh);
+        return;
+    }
+    T F = T(1);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int bot = b * 8;
+        const int top = (bot + 7 < DC - 1) ? bot + 7 : DC - 1;
+        T d[8], Bv[8];
+#pragma unroll
+        for (int k = bot; k <= top; k++) d[k - bot] = col[k * kFG];
+        Bv[top - bot] = ck[b];
+#pragma unroll
+        for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
+#pragma unroll
+        for (int k = bot; k <= top; k++) {
+            const T t = mul_rn(F, Bv[k - bot]);
+            st_stream(base + (size_t)k * kFG, check_to_bit(t));
+            F = mul_rn(F, d[k - bot]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bit-node (column) pass, dec.cpp:667-693.  One thread = one (bit j, slot f).
 //   P_0 = lratio_j, P_{k+1} = P_k*lr_k; tot = P_last (NaN -> 1); dblk_j = (tot <= 1);
@@ -272,10 +380,11 @@ struct SchedArrays {
 };
 
 __global__ void __launch_bounds__(256)
-assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsigned int *counter_to_zero) {
+assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsigned int *counters_to_zero,
+              unsigned int *admitted /* += frames admitted (host picks the check-pass variant from it) */) {
     const int lane = threadIdx.x & 31;
     const int gl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && counter_to_zero) *counter_to_zero = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counters_to_zero) { counters_to_zero[0] = 0; counters_to_zero[1] = 0; }
     if (gl >= G) return;
     const int g = g0 + gl, slot = g * kFG + lane;
     const uint32_t act = s.actw[g], done = s.donew[g];
@@ -298,6 +407,7 @@ assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsign
     if (take) { s.slot_frame[slot] = (int32_t)idx; s.slot_iter[slot] = 0; }
     else if (is_free) s.slot_frame[slot] = -1;
     if (lane == 0) {
+        if (newf) atomicAdd(admitted, (unsigned)__popc(newf));
         s.actw[g] = act | newf;
         s.donew[g] = 0;
         s.newfw[g] = newf;

@@ -62,15 +62,12 @@ Engine::Engine(const Code &code, int device, int precision, int wave_frames)
     up(&d_col_edge_, code.col_edge);
     chk(cudaMalloc((void **)&d_table_, 256 * sizeof(double)), "cudaMalloc(table)");
     chk(cudaMalloc((void **)&d_next_, sizeof(unsigned long long)), "cudaMalloc(next)");
-    chk(cudaMalloc((void **)&d_counters_, (size_t)kHalves * kRing * sizeof(unsigned)), "cudaMalloc(counters)");
-    chk(cudaMallocHost((void **)&h_counters_, (size_t)kHalves * kRing * sizeof(unsigned)), "cudaMallocHost(counters)");
+    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * 2 * sizeof(unsigned)), "cudaMalloc(counters)");
+    chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * 2 * sizeof(unsigned)), "cudaMallocHost(counters)");
     chk(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_), "cudaDeviceGetAttribute");
-    for (auto &h : ev_) for (auto &e : h) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-    chk(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming), "cudaEventCreate");
-    for (auto &e : join_ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    for (auto &e : ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     for (auto &e : prof_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
     chk(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-    for (auto &st : sub_) chk(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
 Engine::~Engine() {
@@ -80,12 +77,9 @@ Engine::~Engine() {
                     d_slot_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
-    for (auto &h : ev_) for (auto &e : h) if (e) cudaEventDestroy(e);
-    if (fork_ev_) cudaEventDestroy(fork_ev_);
-    for (auto &e : join_ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
-    for (auto &st : sub_) if (st) cudaStreamDestroy(st);
 }
 
 int Engine::ensure_slots(int G, bool want_post) {
@@ -142,7 +136,17 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         if (minsum_) row_pass_kernel<T, DC, EX, ALG_MINSUM><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G); \
         else row_pass_kernel<T, DC, EX, ALG_BP><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);         \
     } while (0)
-    if (reg_rows_ && max_row_deg_ == 72) ROW(72, true);
+    static const bool no_smem = getenv("DNALDPC_ROW_REGS") != nullptr;  // A/B switch: register-resident check kernel
+    if (!no_smem && steady_ && reg_rows_ && max_row_deg_ == 72 && !minsum_ && sizeof(T) == 8) {
+        // the (.,72)-regular sum-product hot path: check messages staged in shared memory by TMA, 12 warps per SM
+        const size_t smem = (size_t)kRowWarps * 72 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
+        bool &attr_set = smem_attr_set_[sizeof(T) == 4];
+        if (!attr_set) {  // per engine (= per device)
+            CK(cudaFuncSetAttribute(row_pass_smem_kernel<T, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        row_pass_smem_kernel<T, 72><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G);
+    } else if (reg_rows_ && max_row_deg_ == 72) ROW(72, true);
     else if (max_row_deg_ <= 8) ROW(8, false);
     else if (max_row_deg_ <= 32) ROW(32, false);
     else if (max_row_deg_ <= 72) ROW(72, false);
@@ -255,60 +259,44 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
     init_sched_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(s, G);
     stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kHalves * kRing * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kRing * 2 * sizeof(unsigned), st));
+    steady_ = false;
 
-    // Two halves of the slot groups tick independently on their own streams and pull frames from one shared
-    // counter: the tail of one half's kernel is filled by the other half's next kernel (profiling: one half).
-    const int nh = (!profiling && G >= kHalves * kMinGroupsPerHalf) ? kHalves : 1;
-    int hg0[kHalves], hgn[kHalves];
-    cudaStream_t hs[kHalves];
-    bool live[kHalves];
-    for (int h = 0; h < nh; h++) {
-        hg0[h] = (int)((long long)G * h / nh);
-        hgn[h] = (int)((long long)G * (h + 1) / nh) - hg0[h];
-        hs[h] = nh == 1 ? st : sub_[h];
-        live[h] = true;
-    }
-    if (nh > 1) {
-        CK(cudaEventRecord(fork_ev_, st));
-        for (int h = 0; h < nh; h++) CK(cudaStreamWaitEvent(hs[h], fork_ev_, 0));
-    }
+    // One tick = admit/harvest/check (twice) + one check-node pass + one bit-node pass over all slots.
+    // (Measured alternative, removed: two halves of the groups ticking on two streams so that one half's kernel tail is
+    // filled by the other's next kernel: +0.4 % with the register-resident check kernel, -3 % with the smem-staged one.)
     for (long long tick = 0;; tick++) {
-        bool any = false;
-        for (int h = 0; h < nh; h++) {
-            if (!live[h]) continue;
-            unsigned *ring = d_counters_ + (size_t)h * kRing;
-            unsigned *cnt = ring + tick % kRing;
-            // Two admission rounds per tick: slots that finish in round 1 (incl. frames that need no iteration at all)
-            // are harvested and refilled at once, so a slot idles at most in the rare case of two finishes in a row.
-            for (int round = 1; round <= 2; round++) {
-                assign_kernel<<<(hgn[h] + 7) / 8, 256, 0, hs[h]>>>(s, (long long)F, hg0[h], hgn[h], round == 1,
-                                                                  round == 1 ? ring + (tick + kRing / 2) % kRing : nullptr);
-                stats.kernel_launches++;
-                rc = launch_harvest_setup<T>(in, out, hg0[h], hgn[h], hs[h]);
-                if (rc) return rc;
-                syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)hgn[h]), kSynThreads, 0, hs[h]>>>(
-                    d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, hg0[h], max_iter, round == 2,
-                    (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0,
-                    round == 2 ? cnt : nullptr, (long long)F);
-                stats.kernel_launches++;
-                CK(cudaGetLastError());
-            }
-            CK(cudaMemcpyAsync(h_counters_ + (size_t)h * kRing + tick % kRing, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, hs[h]));
-            CK(cudaEventRecord(ev_[h][tick % kRing], hs[h]));
-            if (tick >= kLag) {  // lagged poll: the host runs at most kLag ticks ahead of the device
-                CK(cudaEventSynchronize(ev_[h][(tick - kLag) % kRing]));
-                if (h_counters_[(size_t)h * kRing + (tick - kLag) % kRing] == 0) { live[h] = false; continue; }  // drained
-            }
-            any = true;
+        unsigned *cnt = d_counters_ + 2 * (tick % kRing);  // [0] busy slots + pending frames, [1] frames admitted this tick
+        // Two admission rounds per tick: slots that finish in round 1 (incl. frames that need no iteration at all)
+        // are harvested and refilled at once, so a slot idles at most in the rare case of two finishes in a row.
+        for (int round = 1; round <= 2; round++) {
+            assign_kernel<<<(G + 7) / 8, 256, 0, st>>>(s, (long long)F, 0, G, round == 1,
+                                                      round == 1 ? d_counters_ + 2 * ((tick + kRing / 2) % kRing) : nullptr, cnt + 1);
+            stats.kernel_launches++;
+            rc = launch_harvest_setup<T>(in, out, 0, G, st);
+            if (rc) return rc;
+            syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(
+                d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, round == 2,
+                (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0, round == 2 ? cnt : nullptr, (long long)F);
+            stats.kernel_launches++;
+            CK(cudaGetLastError());
         }
-        if (!any) break;
+        CK(cudaMemcpyAsync(h_counters_ + 2 * (tick % kRing), cnt, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ev_[tick % kRing], st));
+        if (tick >= kLag) {  // lagged poll: the host runs at most kLag ticks ahead of the device
+            CK(cudaEventSynchronize(ev_[(tick - kLag) % kRing]));
+            const unsigned *hc = h_counters_ + 2 * ((tick - kLag) % kRing);
+            if (hc[0] == 0) break;  // drained: nothing active, finished-unharvested or pending
+            // steady state = every slot busy and nobody being admitted (e.g. long-running frames): the smem-staged
+            // check kernel wins there (+2.5 %); with refills or idle slots the register kernel is faster
+            steady_ = hc[1] == 0 && hc[0] >= (unsigned)G * kFG;
+        }
         if (profiling) CK(cudaEventRecord(prof_ev_[0], st));
-        for (int h = 0; h < nh; h++)
-            if (live[h]) { rc = launch_row<T>(hg0[h], hgn[h], hs[h]); if (rc) return rc; }
+        rc = launch_row<T>(0, G, st);
+        if (rc) return rc;
         if (profiling) CK(cudaEventRecord(prof_ev_[1], st));
-        for (int h = 0; h < nh; h++)
-            if (live[h]) { rc = launch_col<T>(hg0[h], hgn[h], want_post, hs[h]); if (rc) return rc; }
+        rc = launch_col<T>(0, G, want_post, st);
+        if (rc) return rc;
         if (profiling) {
             CK(cudaEventRecord(prof_ev_[2], st));
             CK(cudaEventSynchronize(prof_ev_[2]));
@@ -318,12 +306,6 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
             stats.row_ms += a_ms;
             stats.col_ms += b_ms;
             stats.waves++;  // profiled ticks
-        }
-    }
-    if (nh > 1) {
-        for (int h = 0; h < nh; h++) {
-            CK(cudaEventRecord(join_ev_[h], hs[h]));
-            CK(cudaStreamWaitEvent(st, join_ev_[h], 0));
         }
     }
     return DNALDPC_OK;

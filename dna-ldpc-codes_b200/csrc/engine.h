@@ -49,6 +49,8 @@ class Engine {
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
+    bool smem_attr_set_[2] = {false, false};
+    bool steady_ = false;  // last polled tick: all slots busy, no frame admitted
     bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
     // H edge tables (device)
@@ -64,13 +66,12 @@ class Engine {
     uint8_t *d_ok_ = nullptr;
     int64_t cap_frames_ = 0;
     double *d_table_ = nullptr;                          // 256 doubles (BSC uses the first 2)
-    // progress counters: ring per half, polled kLag ticks behind the device
-    static constexpr int kLag = 2, kRing = 16, kHalves = 2, kMinGroupsPerHalf = 16;
+    // progress counters: a ring, polled kLag ticks behind the device
+    static constexpr int kLag = 2, kRing = 16;
     unsigned int *d_counters_ = nullptr, *h_counters_ = nullptr;
-    cudaEvent_t ev_[kHalves][kRing] = {};
-    cudaEvent_t fork_ev_ = nullptr, join_ev_[kHalves] = {};
+    cudaEvent_t ev_[kRing] = {};
     cudaEvent_t prof_ev_[3] = {};
-    cudaStream_t own_stream_ = nullptr, sub_[kHalves] = {};
+    cudaStream_t own_stream_ = nullptr;
     // staging for the host-pointer path (device side)
     void *s_in_ = nullptr, *s_bits_ = nullptr, *s_dblk_ = nullptr, *s_post_ = nullptr, *s_pchk_ = nullptr;
     size_t c_in_ = 0, c_bits_ = 0, c_dblk_ = 0, c_post_ = 0, c_pchk_ = 0;
