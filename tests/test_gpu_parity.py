@@ -348,3 +348,33 @@ def test_minsum_decoder(code18432, orc18432, cws):
     o = orc18432.decode_minsum(k[2].astype(np.float64) * np.log((1 - 0.02) / 0.02), 60)
     assert a["iters"][2] == o["n"] and np.array_equal(a["bits"][2], o["dblk"])
     dec.close()
+
+
+def test_scheduler_fuzz_small_code():
+    """Continuous batching under many shapes: every frame of every batch against the oracle (bits, n, flag, posterior),
+    on the small (N=120) code where the oracle is cheap. Covers F < slots, F >> slots, ragged groups, frames that need
+    no iteration, max_iter 0/1, and both algorithms."""
+    path = os.path.join(ol.GOLDEN, "small_n120_m60.pchk")
+    code = ldpc.Code(path)
+    orc = ol.Oracle(path)
+    rs = np.random.RandomState(2027)
+    Nn = 120
+    for wave, F, mi in [(32, 1, 20), (32, 33, 20), (64, 500, 30), (96, 97, 5), (32, 200, 0), (64, 130, 1), (128, 1000, 50)]:
+        dec = ldpc.Decoder(code, wave_frames=wave)
+        q = rs.choice([0.0, 0.02, 0.06, 0.10], size=F)              # per-frame channel quality; 0.0 = noiseless (n = 0)
+        flips = rs.rand(F, Nn) < q[:, None]
+        amp = rs.uniform(0.5, 6.0, (F, Nn))
+        llr = np.where(flips, -1.0, 1.0) * amp                      # all-zero codeword
+        llr[rs.rand(F, Nn) < 0.03] = 0.0                            # erasures: LR exactly 1, LLR exactly 0
+        lr = np.exp(llr)
+        r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=("bits", "iters", "ok", "post", "pchk"))
+        m = dec.decode(ldpc.IN_LLR_F64, llr, mi, flags=ldpc.FLAG_MINSUM, want=("bits", "iters", "ok", "post"))
+        for f in range(F):
+            o = orc.decode(lr[f], mi)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (wave, F, mi, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (wave, F, mi, f)
+            assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, F, mi, f)
+            o = orc.decode_minsum(llr[f], mi)
+            assert m["iters"][f] == o["n"] and m["ok"][f] == o["ok"] and np.array_equal(m["bits"][f], o["dblk"]), (wave, F, mi, f)
+            assert np.array_equal(m["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, F, mi, f)
+        dec.close()
