@@ -188,6 +188,12 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    # in-pipeline trace (no synchronisation): real per-tick check-pass / bit-pass / scheduler times of a warm-up step
+    dec.set_profiling(2)
+    step_device()
+    torch.cuda.synchronize()
+    tr_row, tr_col, tr_sched, tr_ticks = dec.trace()
+    dec.set_profiling(0)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -261,6 +267,8 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src, "launch_ms": kms, "frames_per_launch": frames_per_launch,
             "row_ms": row_ms, "col_ms": col_ms,
+            "in_pipeline": {"row_ms": tr_row, "col_ms": tr_col, "scheduler_ms": tr_sched, "ticks": tr_ticks,
+                            "note": "CUDA events inside the running pipeline (no sync): check pass, bit pass, and bit-pass end -> next check-pass start"},
             "iteration": {"achieved": bscale * B_ITER * frames_per_launch / ((row_ms + col_ms) * 1e-3) / 1e9,
                           "note": "B_iter=32E+8.25N per frame-iteration over row+col kernel time"},
             "whole_step": {"achieved": bscale * B_ITER * (frame_iters_all / world) / (ms / args.steps * 1e-3) / 1e9,

@@ -25,7 +25,7 @@ EXPORTS = [
     "dnaldpc_code_check_regular", "dnaldpc_decoder_create", "dnaldpc_decoder_destroy", "dnaldpc_decode_batch",
     "dnaldpc_decode_batch_device", "dnaldpc_run_bp_decoder", "dnaldpc_std_dev", "dnaldpc_vote_table",
     "dnaldpc_bsc_table", "dnaldpc_synth_bsc_device", "dnaldpc_get_stats", "dnaldpc_set_profiling",
-    "dnaldpc_selftest_math", "dnaldpc_redecode_sweep",
+    "dnaldpc_selftest_math", "dnaldpc_redecode_sweep", "dnaldpc_get_trace",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         L.dnaldpc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.dnaldpc_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.dnaldpc_selftest_math.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.dnaldpc_get_trace.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.dnaldpc_redecode_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.POINTER(Output), C.c_void_p]
         _lib = L
@@ -238,6 +239,12 @@ class Decoder:
 
     def set_profiling(self, on):
         _check(lib().dnaldpc_set_profiling(self._h, int(on)))
+
+    def trace(self):
+        """(row_ms, col_ms, sched_ms, ticks) of the in-pipeline trace armed by set_profiling(2)."""
+        r, c, g, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        _check(lib().dnaldpc_get_trace(self._h, C.byref(r), C.byref(c), C.byref(g), C.byref(n)))
+        return r.value, c.value, g.value, n.value
 
 
 def selftest_math(n, seed=1):

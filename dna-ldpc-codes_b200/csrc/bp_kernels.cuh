@@ -380,11 +380,10 @@ struct SchedArrays {
 };
 
 __global__ void __launch_bounds__(256)
-assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round, unsigned int *counters_to_zero,
-              unsigned int *admitted /* += frames admitted (host picks the check-pass variant from it) */) {
+assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round,
+              unsigned int *admitted /* += frames admitted (the host schedules the next ticks from it) */) {
     const int lane = threadIdx.x & 31;
     const int gl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && counters_to_zero) { counters_to_zero[0] = 0; counters_to_zero[1] = 0; }
     if (gl >= G) return;
     const int g = g0 + gl, slot = g * kFG + lane;
     const uint32_t act = s.actw[g], done = s.donew[g];
@@ -431,8 +430,15 @@ __global__ void __launch_bounds__(kSynThreads)
 syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t *__restrict__ iters_out,
                        uint8_t *__restrict__ ok_out, const int32_t *__restrict__ row_ptr,
                        const int32_t *__restrict__ col_idx, int M, int N, int g0, int max_iter, int consider_new, int fixed_iters,
-                       unsigned int *__restrict__ counter /* += slots still busy (active or awaiting harvest), or NULL */,
+                       unsigned int *__restrict__ counter /* [0] += slots still busy (active or awaiting harvest) + pending
+                                                             frames, or NULL when a later launch of the tick counts */,
+                       unsigned int *__restrict__ finished /* += frames that finished in this launch */,
+                       unsigned int *__restrict__ counters_to_zero /* ring entry (3 words) re-armed for a later tick, or NULL */,
+                       int clear_fresh /* tick without admission: no assign_kernel will reset the fresh marks */,
                        long long F) {
+    if (counters_to_zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        counters_to_zero[0] = 0; counters_to_zero[1] = 0; counters_to_zero[2] = 0;
+    }
     const int g = g0 + blockIdx.y;
     const uint32_t act = s.actw[g];
     const uint32_t consider = consider_new ? s.newfw[g] : act;
@@ -506,6 +512,8 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t
             s.donew[g] = dn;
             s.unsatw[g] = 0;  // re-armed
             s.arrive[g] = 0;
+            if (clear_fresh) s.freshw[g] = 0;  // every slot admitted earlier has had its first check pass
+            if (done) atomicAdd(finished, (unsigned)__popc(done));
             if (counter) {
                 unsigned add = (unsigned)(__popc(still) + __popc(dn));
                 if (blockIdx.y == 0) {

@@ -327,7 +327,14 @@ int dnaldpc_get_stats(const dnaldpc_decoder *d, dnaldpc_stats *s) {
 
 int dnaldpc_set_profiling(dnaldpc_decoder *d, int on) {
     if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
-    for (auto &e : d->eng) e->profiling = on != 0;
+    for (auto &e : d->eng) { e->profiling = on == 1; e->trace_ticks_ = on == 2 ? 64 : 0; }
+    return DNALDPC_OK;
+}
+
+int dnaldpc_get_trace(dnaldpc_decoder *d, double *row_ms, double *col_ms, double *sched_ms, int *ticks) {
+    if (!d || !row_ms || !col_ms || !sched_ms) return set_err(DNALDPC_ERR_ARG, "null argument");
+    const int n = d->eng[0]->trace_result(row_ms, col_ms, sched_ms);
+    if (ticks) *ticks = n;
     return DNALDPC_OK;
 }
 

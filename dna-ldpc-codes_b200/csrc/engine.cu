@@ -62,11 +62,12 @@ Engine::Engine(const Code &code, int device, int precision, int wave_frames)
     up(&d_col_edge_, code.col_edge);
     chk(cudaMalloc((void **)&d_table_, 256 * sizeof(double)), "cudaMalloc(table)");
     chk(cudaMalloc((void **)&d_next_, sizeof(unsigned long long)), "cudaMalloc(next)");
-    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * 2 * sizeof(unsigned)), "cudaMalloc(counters)");
-    chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * 2 * sizeof(unsigned)), "cudaMallocHost(counters)");
+    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * 3 * sizeof(unsigned)), "cudaMalloc(counters)");
+    chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * 3 * sizeof(unsigned)), "cudaMallocHost(counters)");
     chk(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_), "cudaDeviceGetAttribute");
     for (auto &e : ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     for (auto &e : prof_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
+    for (auto &e : trace_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
     chk(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
@@ -79,6 +80,7 @@ Engine::~Engine() {
     if (h_counters_) cudaFreeHost(h_counters_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : trace_ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -259,44 +261,65 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
     init_sched_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(s, G);
     stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kRing * 2 * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kRing * 3 * sizeof(unsigned), st));
     steady_ = false;
+    traced_ = 0;
 
     // One tick = admit/harvest/check (twice) + one check-node pass + one bit-node pass over all slots.
     // (Measured alternative, removed: two halves of the groups ticking on two streams so that one half's kernel tail is
     // filled by the other's next kernel: +0.4 % with the register-resident check kernel, -3 % with the smem-staged one.)
+    unsigned last_busy = 0, last_admitted = 1, last_finished = 1;  // what the host knows (kLag ticks old)
     for (long long tick = 0;; tick++) {
-        unsigned *cnt = d_counters_ + 2 * (tick % kRing);  // [0] busy slots + pending frames, [1] frames admitted this tick
-        // Two admission rounds per tick: slots that finish in round 1 (incl. frames that need no iteration at all)
-        // are harvested and refilled at once, so a slot idles at most in the rare case of two finishes in a row.
-        for (int round = 1; round <= 2; round++) {
-            assign_kernel<<<(G + 7) / 8, 256, 0, st>>>(s, (long long)F, 0, G, round == 1,
-                                                      round == 1 ? d_counters_ + 2 * ((tick + kRing / 2) % kRing) : nullptr, cnt + 1);
-            stats.kernel_launches++;
-            rc = launch_harvest_setup<T>(in, out, 0, G, st);
-            if (rc) return rc;
+        // ring entry of this tick: [0] busy slots + pending frames, [1] frames admitted, [2] frames finished
+        unsigned *cnt = d_counters_ + 3 * (tick % kRing);
+        unsigned *rearm = d_counters_ + 3 * ((tick + kRing / 2) % kRing);
+        const int fixed = (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0;
+        // Admission (assign + harvest/setup, twice) is only launched when the host has reason to expect work for it:
+        // start-up, a frame finished or was admitted kLag ticks ago, or slots are idle. In the steady state of long
+        // frames a tick is just syndrome -> check pass -> bit pass; a finish is then picked up at most kLag ticks late.
+        const bool admit = tick < 2 + kLag || last_finished > 0 || last_admitted > 0 || last_busy < (unsigned)G * kFG;
+        if (admit) {
+            // Two admission rounds: slots that finish in round 1 (incl. frames that need no iteration at all) are
+            // harvested and refilled at once, so a slot idles at most in the rare case of two finishes in a row.
+            for (int round = 1; round <= 2; round++) {
+                assign_kernel<<<(G + 7) / 8, 256, 0, st>>>(s, (long long)F, 0, G, round == 1, cnt + 1);
+                stats.kernel_launches++;
+                rc = launch_harvest_setup<T>(in, out, 0, G, st);
+                if (rc) return rc;
+                syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(
+                    d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, round == 2, fixed,
+                    round == 2 ? cnt : nullptr, cnt + 2, round == 1 ? rearm : nullptr, 0, (long long)F);
+                stats.kernel_launches++;
+                CK(cudaGetLastError());
+            }
+        } else {
             syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(
-                d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, round == 2,
-                (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0, round == 2 ? cnt : nullptr, (long long)F);
+                d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, 0, fixed, cnt, cnt + 2,
+                rearm, 1, (long long)F);
             stats.kernel_launches++;
             CK(cudaGetLastError());
         }
-        CK(cudaMemcpyAsync(h_counters_ + 2 * (tick % kRing), cnt, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_counters_ + 3 * (tick % kRing), cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev_[tick % kRing], st));
         if (tick >= kLag) {  // lagged poll: the host runs at most kLag ticks ahead of the device
             CK(cudaEventSynchronize(ev_[(tick - kLag) % kRing]));
-            const unsigned *hc = h_counters_ + 2 * ((tick - kLag) % kRing);
-            if (hc[0] == 0) break;  // drained: nothing active, finished-unharvested or pending
+            const unsigned *hc = h_counters_ + 3 * ((tick - kLag) % kRing);
+            last_busy = hc[0]; last_admitted = hc[1]; last_finished = hc[2];
+            if (last_busy == 0) break;  // drained: nothing active, finished-unharvested or pending
             // steady state = every slot busy and nobody being admitted (e.g. long-running frames): the smem-staged
             // check kernel wins there (+2.5 %); with refills or idle slots the register kernel is faster
-            steady_ = hc[1] == 0 && hc[0] >= (unsigned)G * kFG;
+            steady_ = last_admitted == 0 && last_busy >= (unsigned)G * kFG;
         }
+        const bool trace = trace_ticks_ > 0 && tick >= 8 && tick < 8 + kTrace && tick < 8 + trace_ticks_;  // in-pipeline timing, no sync
+        if (trace) CK(cudaEventRecord(trace_ev_[3 * (tick - 8)], st));
         if (profiling) CK(cudaEventRecord(prof_ev_[0], st));
         rc = launch_row<T>(0, G, st);
         if (rc) return rc;
         if (profiling) CK(cudaEventRecord(prof_ev_[1], st));
+        if (trace) CK(cudaEventRecord(trace_ev_[3 * (tick - 8) + 1], st));
         rc = launch_col<T>(0, G, want_post, st);
         if (rc) return rc;
+        if (trace) { CK(cudaEventRecord(trace_ev_[3 * (tick - 8) + 2], st)); traced_ = (int)(tick - 8) + 1; }
         if (profiling) {
             CK(cudaEventRecord(prof_ev_[2], st));
             CK(cudaEventSynchronize(prof_ev_[2]));
@@ -309,6 +332,25 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
         }
     }
     return DNALDPC_OK;
+}
+
+// In-pipeline timing of ticks 8..8+n (events recorded without any synchronisation; call after the stream has drained):
+// average check-pass, bit-pass and scheduler (bit-pass end -> next check-pass start) time per tick in ms.
+int Engine::trace_result(double *row_ms, double *col_ms, double *sched_ms) {
+    *row_ms = *col_ms = *sched_ms = 0;
+    if (traced_ < 2) return 0;
+    CK(cudaSetDevice(device_));
+    CK(cudaEventSynchronize(trace_ev_[3 * (traced_ - 1) + 2]));
+    double r = 0, c = 0, g = 0;
+    for (int t = 0; t < traced_; t++) {
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, trace_ev_[3 * t], trace_ev_[3 * t + 1]);
+        cudaEventElapsedTime(&b, trace_ev_[3 * t + 1], trace_ev_[3 * t + 2]);
+        if (t + 1 < traced_) cudaEventElapsedTime(&d, trace_ev_[3 * t + 2], trace_ev_[3 * (t + 1)]);
+        r += a; c += b; g += d;
+    }
+    *row_ms = r / traced_; *col_ms = c / traced_; *sched_ms = g / (traced_ - 1);
+    return traced_;
 }
 
 int Engine::decode_device(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out, cudaStream_t stream) {

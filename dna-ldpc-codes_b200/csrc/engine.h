@@ -32,6 +32,8 @@ class Engine {
 
     dnaldpc_stats stats{};
     bool profiling = false;
+    int trace_ticks_ = 0;  // > 0: record in-pipeline events for that many ticks of the next batch (no synchronisation)
+    int trace_result(double *row_ms, double *col_ms, double *sched_ms);
 
   private:
     template <typename T> int run(const dnaldpc_input &in_dev, int64_t F, int max_iter, const dnaldpc_output &out_dev, cudaStream_t st);
@@ -71,6 +73,9 @@ class Engine {
     unsigned int *d_counters_ = nullptr, *h_counters_ = nullptr;
     cudaEvent_t ev_[kRing] = {};
     cudaEvent_t prof_ev_[3] = {};
+    static constexpr int kTrace = 64;
+    cudaEvent_t trace_ev_[3 * kTrace] = {};
+    int traced_ = 0;
     cudaStream_t own_stream_ = nullptr;
     // staging for the host-pointer path (device side)
     void *s_in_ = nullptr, *s_bits_ = nullptr, *s_dblk_ = nullptr, *s_post_ = nullptr, *s_pchk_ = nullptr;

@@ -163,8 +163,13 @@ typedef struct dnaldpc_stats {
     double total_ms;
 } dnaldpc_stats;
 int dnaldpc_get_stats(const dnaldpc_decoder *d, dnaldpc_stats *s);
-/* 1 = bracket the row/column kernels of each iteration with CUDA events (adds host syncs; benchmarking only) */
+/* 1 = bracket the row/column kernels of each iteration with CUDA events (adds host syncs; benchmarking only);
+ * 2 = in-pipeline trace: events around the check pass / bit pass of ticks 8..71 of the next batch, NO synchronisation
+ *     (first device only); read with dnaldpc_get_trace after the batch. 0 = off. */
 int dnaldpc_set_profiling(dnaldpc_decoder *d, int on);
+/* Average check-pass, bit-pass and scheduler (bit-pass end -> next check-pass start: syndrome, admission, launch gaps)
+ * time per traced tick, in ms. */
+int dnaldpc_get_trace(dnaldpc_decoder *d, double *row_ms, double *col_ms, double *sched_ms, int *ticks);
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 /* Runs `n` random operands (plus the IEEE corner cases) through the inlined in-range reciprocal / division sequences
