@@ -205,8 +205,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 // warp lands the contiguous run in the warp's tile, the factors d_k overwrite the tile in place, and only the 9
 // check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
 // <= 168 registers: 12 warps (3 CTAs, 3 x 73.8 KB of shared memory) per SM instead of 8, i.e. 50 % more bytes in flight.
-// Slots that start a frame then overwrite their column with gathered channel ratios; groups with idle slots (drain
-// tail: finished lanes must not be loaded or stored) fill the tile lane by lane instead.
+// Groups with a slot that starts a frame or with idle slots fill the tile lane by lane with cp.async instead.
 template <typename T, int DC>
 __global__ void __launch_bounds__(kRowWarps * 32, 3)
 row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
@@ -228,7 +227,7 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
     T *base = msg + ((size_t)g * E + e0) * kFG + lane;
     T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
     const T *lr_lane = lratio + (size_t)g * N * kFG + lane;
-    if (act == 0xffffffffu) {  // warp-uniform: every slot of the group is busy -> one bulk copy for the whole tile
+    if (act == 0xffffffffu && fw == 0) {  // warp-uniform: full group, nobody starts a frame -> one bulk copy
         if (lane == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
@@ -237,15 +236,19 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
         }
         __syncwarp();
         mbar_wait(bar, 0);
-        if (fresh) {  // slots that start a frame replace their column by the channel ratios of the check's bits
-#pragma unroll 24
-            for (int k = 0; k < DC; k++) col[k * kFG] = lr_lane[(size_t)__ldg(col_idx + e0 + k) * kFG];
-        }
-    } else {  // drain tail: finished / empty lanes must not be loaded or stored
+    } else {
+        // Mixed group: every active lane fills its own column with asynchronous 8-byte copies (cp.async / LDGSTS): a
+        // slot that starts a frame takes the channel ratios of the check's bits (Init_Belief_Propagation), the others
+        // their messages; finished / empty lanes copy nothing. All DC copies of a lane are in flight at once and, as
+        // with the bulk copy, none of them occupies a register.
         if (!on) return;
-#pragma unroll 24
-        for (int k = 0; k < DC; k++)
-            col[k * kFG] = fresh ? lr_lane[(size_t)__ldg(col_idx + e0 + k) * kFG] : ld_stream(base + (size_t)k * kFG);
+#pragma unroll 12
+        for (int k = 0; k < DC; k++) {
+            const T *src = fresh ? lr_lane + (size_t)__ldg(col_idx + e0 + k) * kFG : base + (size_t)k * kFG;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(col + k * kFG)), "l"(src), "n"(sizeof(T)) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     // pass 1, descending: d_k in place, backward products check-pointed every 8 edges
     constexpr int NB = (DC + 7) / 8;

@@ -139,7 +139,8 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         else row_pass_kernel<T, DC, EX, ALG_BP><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);         \
     } while (0)
     static const bool no_smem = getenv("DNALDPC_ROW_REGS") != nullptr;  // A/B switch: register-resident check kernel
-    if (!no_smem && steady_ && reg_rows_ && max_row_deg_ == 72 && !minsum_ && sizeof(T) == 8) {
+    static const bool always_smem = getenv("DNALDPC_ROW_SMEM_ALWAYS") != nullptr;  // A/B switch
+    if (!no_smem && (steady_ || always_smem) && reg_rows_ && max_row_deg_ == 72 && !minsum_ && sizeof(T) == 8) {
         // the (.,72)-regular sum-product hot path: check messages staged in shared memory by TMA, 12 warps per SM
         const size_t smem = (size_t)kRowWarps * 72 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
         bool &attr_set = smem_attr_set_[sizeof(T) == 4];

@@ -378,3 +378,34 @@ def test_scheduler_fuzz_small_code():
             assert m["iters"][f] == o["n"] and m["ok"][f] == o["ok"] and np.array_equal(m["bits"][f], o["dblk"]), (wave, F, mi, f)
             assert np.array_equal(m["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, F, mi, f)
         dec.close()
+
+
+def test_smem_check_kernel_mixed_groups_in_subprocess():
+    """The shared-memory check kernel normally runs only in the steady state (full groups, nobody admitted). Its
+    cp.async path for mixed groups (fresh / idle lanes) is forced here with the A/B switch, in a child process
+    because the switch is read once per process, and compared frame by frame with the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import _pkg, oraclelib as ol
+ldpc = _pkg.load()
+N = 18432
+cws = ol.load_codewords(); orc = ol.Oracle(ol.PCHK_18432)
+dec = ldpc.Decoder(ldpc.Code(ol.PCHK_18432), wave_frames=64)
+F = 150
+eps_of = [0.004, 0.006, 0.0075, 0.0085]
+lr = np.stack([np.where((cws[f] ^ ol.bsc_flips(33, f, N, eps_of[f % 4])) == 0, (1 - eps_of[f % 4]) / eps_of[f % 4], eps_of[f % 4] / (1 - eps_of[f % 4])) for f in range(F)])
+r = dec.decode(ldpc.IN_LR_F64, lr, 25, want=("bits", "iters", "ok", "post"))
+for f in range(0, F, 4):
+    o = orc.decode(lr[f], 25)
+    assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"] and np.array_equal(r["bits"][f], o["dblk"]), f
+    assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
+print("ok", sorted(set(r["iters"].tolist()))[:6])
+'''
+    env = dict(os.environ, DNALDPC_ROW_SMEM_ALWAYS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.startswith("ok"), res.stdout + res.stderr
