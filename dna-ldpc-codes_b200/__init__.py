@@ -46,7 +46,8 @@ class Output(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_int64), ("frame_iters", C.c_int64), ("kernel_launches", C.c_int64),
-                ("waves", C.c_int64), ("row_ms", C.c_double), ("col_ms", C.c_double), ("total_ms", C.c_double)]
+                ("waves", C.c_int64), ("row_ms", C.c_double), ("col_ms", C.c_double), ("total_ms", C.c_double),
+                ("compactions", C.c_int64)]
 
 
 class LdpcError(RuntimeError):

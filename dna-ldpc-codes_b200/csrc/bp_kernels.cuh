@@ -670,6 +670,89 @@ syndrome_bytes_kernel(const uint32_t *__restrict__ decw, SchedArrays s, const in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Slot scheduler, part 3: compaction of the drain tail. Once no frame is pending, finished slots are not refilled and
+// the stragglers end up spread thinly over all groups: a warp of the check/bit pass with 3 of its 32 lanes active
+// still issues every request, each for one 32 B sector. compact_plan_kernel (one warp) picks the smallest K such that
+// the free slots of groups [0,K) can take every active slot of groups [K,G), pairs them by rank and moves the slot
+// bookkeeping; compact_move_kernel copies the two per-slot arrays that carry state across a tick (messages and
+// channel ratios; decisions and posteriors are rewritten by the next bit pass before anything reads them).
+// Runs between the syndrome/loop-control kernel and the check pass. Slots awaiting harvest are neither moved nor used
+// as destinations. Results are unaffected: frames are independent and outputs are written by frame index.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+compact_plan_kernel(SchedArrays s, int G, int32_t *__restrict__ mv_src, int32_t *__restrict__ mv_dst,
+                    int32_t *__restrict__ mv_count /* [0] = number of moves, [1] = K */) {
+    const int lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1u;
+    int above = 0;
+    for (int g = lane; g < G; g += 32) above += __popc(s.actw[g]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    int K = 0, free_below = 0;
+    while (K < G && free_below < above) {  // warp-uniform
+        const uint32_t a = s.actw[K], d = s.donew[K];
+        above -= __popc(a);
+        free_below += __popc(~(a | d));
+        K++;
+    }
+    int nsrc = 0;
+    for (int g = K; g < G; g++) {
+        const uint32_t a = s.actw[g];
+        if ((a >> lane) & 1u) mv_src[nsrc + __popc(a & lt)] = g * kFG + lane;
+        nsrc += __popc(a);
+    }
+    int ndst = 0;
+    for (int g = 0; g < K && ndst < nsrc; g++) {
+        const uint32_t fr = ~(s.actw[g] | s.donew[g]);
+        if ((fr >> lane) & 1u) mv_dst[ndst + __popc(fr & lt)] = g * kFG + lane;
+        ndst += __popc(fr);
+    }
+    __threadfence_block();
+    __syncwarp();
+    for (int m = lane; m < nsrc; m += 32) {
+        const int src = mv_src[m], dst = mv_dst[m];
+        const uint32_t sb = 1u << (src & 31), db = 1u << (dst & 31);
+        atomicAnd(s.actw + (src >> 5), ~sb);
+        atomicOr(s.actw + (dst >> 5), db);
+        if (atomicAnd(s.freshw + (src >> 5), ~sb) & sb) atomicOr(s.freshw + (dst >> 5), db);
+        else atomicAnd(s.freshw + (dst >> 5), ~db);
+        s.slot_frame[dst] = s.slot_frame[src];
+        s.slot_iter[dst] = s.slot_iter[src];
+        s.slot_frame[src] = -1;
+    }
+    if (lane == 0) { mv_count[0] = nsrc; mv_count[1] = K; }
+}
+
+constexpr int kMoveThreads = 256, kMoveUnroll = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kMoveThreads)
+compact_move_kernel(T *__restrict__ msg, T *__restrict__ lratio, const int32_t *__restrict__ mv_src,
+                    const int32_t *__restrict__ mv_dst, const int32_t *__restrict__ mv_count, int N, int E) {
+    const int nmv = mv_count[0];
+    for (int m = blockIdx.y; m < nmv; m += gridDim.y) {
+        const int src = mv_src[m], dst = mv_dst[m];
+        const T *ms = msg + (size_t)(src >> 5) * E * kFG + (src & 31);
+        T *md = msg + (size_t)(dst >> 5) * E * kFG + (dst & 31);
+        const T *ls = lratio + (size_t)(src >> 5) * N * kFG + (src & 31);
+        T *ld = lratio + (size_t)(dst >> 5) * N * kFG + (dst & 31);
+        const int base = blockIdx.x * (kMoveThreads * kMoveUnroll) + threadIdx.x;
+        T v[kMoveUnroll];
+#pragma unroll
+        for (int u = 0; u < kMoveUnroll; u++) {
+            const int x = base + u * kMoveThreads;
+            v[u] = x < E ? ms[(size_t)x * kFG] : (x < E + N ? ls[(size_t)(x - E) * kFG] : T(0));
+        }
+#pragma unroll
+        for (int u = 0; u < kMoveUnroll; u++) {
+            const int x = base + u * kMoveThreads;
+            if (x < E) md[(size_t)x * kFG] = v[u];
+            else if (x < E + N) ld[(size_t)(x - E) * kFG] = v[u];
+        }
+    }
+}
+
 __global__ void init_sched_kernel(SchedArrays s, int G) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < G * kFG) { s.slot_frame[t] = -1; s.slot_iter[t] = 0; s.harv_frame[t] = -1; s.harv_iter[t] = 0; }

@@ -198,6 +198,7 @@ int dnaldpc_decode_batch(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F,
         const dnaldpc_stats &s = d->eng[k]->stats;
         d->stats.frames += s.frames; d->stats.frame_iters += s.frame_iters; d->stats.kernel_launches += s.kernel_launches;
         d->stats.waves += s.waves; d->stats.row_ms += s.row_ms; d->stats.col_ms += s.col_ms;
+        d->stats.compactions += s.compactions;
     }
     return DNALDPC_OK;
 }

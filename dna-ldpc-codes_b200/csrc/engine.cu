@@ -75,7 +75,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
-                    d_slot_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
+                    d_slot_, d_mv_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
@@ -86,9 +86,9 @@ Engine::~Engine() {
 
 int Engine::ensure_slots(int G, bool want_post) {
     if (G > cap_groups_) {
-        void *ptrs[] = {d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_, d_slot_};
+        void *ptrs[] = {d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_, d_slot_, d_mv_};
         for (void *p : ptrs) if (p) cudaFree(p);
-        d_msg_ = d_lratio_ = d_post_ = nullptr; d_decw_ = d_masks_ = nullptr; d_arrive_ = nullptr; d_slot_ = nullptr;
+        d_msg_ = d_lratio_ = d_post_ = nullptr; d_decw_ = d_masks_ = nullptr; d_arrive_ = nullptr; d_slot_ = d_mv_ = nullptr;
         cap_groups_ = 0;
         CK(cudaMalloc(&d_msg_, std::max<size_t>((size_t)G * E_ * kFG * esz_, 16)));
         CK(cudaMalloc(&d_lratio_, (size_t)G * N_ * kFG * esz_));
@@ -96,6 +96,7 @@ int Engine::ensure_slots(int G, bool want_post) {
         CK(cudaMalloc((void **)&d_masks_, (size_t)G * 6 * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&d_arrive_, (size_t)G * sizeof(unsigned)));
         CK(cudaMalloc((void **)&d_slot_, (size_t)G * kFG * 4 * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&d_mv_, ((size_t)G * kFG * 2 + 2) * sizeof(int32_t)));
         cap_groups_ = G;
     }
     if (want_post && !d_post_) CK(cudaMalloc(&d_post_, (size_t)cap_groups_ * N_ * kFG * esz_));
@@ -270,6 +271,14 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
     // (Measured alternative, removed: two halves of the groups ticking on two streams so that one half's kernel tail is
     // filled by the other's next kernel: +0.4 % with the register-resident check kernel, -3 % with the smem-staged one.)
     unsigned last_busy = 0, last_admitted = 1, last_finished = 1;  // what the host knows (kLag ticks old)
+    // Drain tail: once every frame has been admitted (sum of the polled `admitted` counters == F) finished slots stay
+    // empty and the stragglers thin out over all groups; whenever fewer than kCompactFrac of the slots of the packed
+    // region are still busy they are compacted into the lowest groups (compact_*_kernel) and the check / bit passes
+    // shrink to those groups.
+    const bool no_compact = getenv("DNALDPC_NO_COMPACT") != nullptr;  // A/B switch, read per batch
+    long long admitted_total = 0;
+    int G_rc = G;                             // groups the check / bit passes are launched over
+    long long packed_cap = (long long)G * kFG;  // slots of the region the busy slots were last packed into
     for (long long tick = 0;; tick++) {
         // ring entry of this tick: [0] busy slots + pending frames, [1] frames admitted, [2] frames finished
         unsigned *cnt = d_counters_ + 3 * (tick % kRing);
@@ -310,15 +319,30 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
             // steady state = every slot busy and nobody being admitted (e.g. long-running frames): the smem-staged
             // check kernel wins there (+2.5 %); with refills or idle slots the register kernel is faster
             steady_ = last_admitted == 0 && last_busy >= (unsigned)G * kFG;
+            admitted_total += last_admitted;
+            if (!no_compact && !profiling && admitted_total >= F && packed_cap >= 2 * kFG &&
+                (long long)last_busy * kCompactDen <= packed_cap * kCompactNum) {
+                // `last_busy` is kLag ticks old and can only have shrunk since: it bounds the moves and the packed size
+                int32_t *mv_src = d_mv_, *mv_dst = d_mv_ + (size_t)cap_groups_ * kFG, *mv_cnt = d_mv_ + (size_t)cap_groups_ * kFG * 2;
+                compact_plan_kernel<<<1, 32, 0, st>>>(s, G, mv_src, mv_dst, mv_cnt);
+                dim3 mgrid((unsigned)((E_ + N_ + kMoveThreads * kMoveUnroll - 1) / (kMoveThreads * kMoveUnroll)),
+                           (unsigned)std::min<unsigned>(last_busy, 2048u));
+                compact_move_kernel<T><<<mgrid, kMoveThreads, 0, st>>>((T *)d_msg_, (T *)d_lratio_, mv_src, mv_dst, mv_cnt, N_, E_);
+                stats.kernel_launches += 2;
+                stats.compactions++;
+                CK(cudaGetLastError());
+                G_rc = (int)std::min<long long>(G, ((long long)last_busy + kFG - 1) / kFG);
+                packed_cap = (long long)G_rc * kFG;
+            }
         }
         const bool trace = trace_ticks_ > 0 && tick >= 8 && tick < 8 + kTrace && tick < 8 + trace_ticks_;  // in-pipeline timing, no sync
         if (trace) CK(cudaEventRecord(trace_ev_[3 * (tick - 8)], st));
         if (profiling) CK(cudaEventRecord(prof_ev_[0], st));
-        rc = launch_row<T>(0, G, st);
+        rc = launch_row<T>(0, G_rc, st);
         if (rc) return rc;
         if (profiling) CK(cudaEventRecord(prof_ev_[1], st));
         if (trace) CK(cudaEventRecord(trace_ev_[3 * (tick - 8) + 1], st));
-        rc = launch_col<T>(0, G, want_post, st);
+        rc = launch_col<T>(0, G_rc, want_post, st);
         if (rc) return rc;
         if (trace) { CK(cudaEventRecord(trace_ev_[3 * (tick - 8) + 2], st)); traced_ = (int)(tick - 8) + 1; }
         if (profiling) {
@@ -433,6 +457,7 @@ int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const 
         acc.waves += stats.waves;
         acc.row_ms += stats.row_ms;
         acc.col_ms += stats.col_ms;
+        acc.compactions += stats.compactions;
         if (out.bits) CK(cudaMemcpyAsync(out.bits + (size_t)f0 * wpf, o.bits, (size_t)nf * wpf * 4, cudaMemcpyDeviceToHost, st));
         if (out.dblk) CK(cudaMemcpyAsync(out.dblk + (size_t)f0 * N_, o.dblk, (size_t)nf * N_, cudaMemcpyDeviceToHost, st));
         if (out.posterior) CK(cudaMemcpyAsync(out.posterior + (size_t)f0 * N_, o.posterior, (size_t)nf * N_ * 8, cudaMemcpyDeviceToHost, st));

@@ -63,6 +63,8 @@ class Engine {
     uint32_t *d_decw_ = nullptr, *d_masks_ = nullptr;  // masks: 6 words per group (act, done, newf, fresh, harv, unsat)
     unsigned int *d_arrive_ = nullptr;
     int32_t *d_slot_ = nullptr;                          // 4 ints per slot (frame, iter, harv_frame, harv_iter)
+    int32_t *d_mv_ = nullptr;                            // drain-tail compaction: src[S], dst[S], {count, K}
+    static constexpr int kCompactNum = 1, kCompactDen = 2;  // compact when busy slots <= 1/2 of the packed region
     unsigned long long *d_next_ = nullptr;
     int32_t *d_iters_ = nullptr;                         // per-frame scratch when the caller does not want them
     uint8_t *d_ok_ = nullptr;

@@ -161,6 +161,7 @@ typedef struct dnaldpc_stats {
     int64_t waves;
     double row_ms, col_ms;   /* device time (CUDA events) inside the check-node / bit-node kernels; 0 unless profiling enabled */
     double total_ms;
+    int64_t compactions;     /* drain-tail compactions (stragglers re-packed into the lowest slot groups) */
 } dnaldpc_stats;
 int dnaldpc_get_stats(const dnaldpc_decoder *d, dnaldpc_stats *s);
 /* 1 = bracket the row/column kernels of each iteration with CUDA events (adds host syncs; benchmarking only);

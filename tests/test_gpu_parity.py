@@ -380,6 +380,37 @@ def test_scheduler_fuzz_small_code():
         dec.close()
 
 
+def test_drain_tail_compaction(code18432, orc18432, cws):
+    """Drain-tail compaction (compact_plan_kernel / compact_move_kernel): once no frame is pending the stragglers are
+    re-packed into the lowest slot groups. 700 frames through 512 slots, 1 frame in 8 far above the threshold so that it
+    runs all 40 iterations while its neighbours finish in a handful: the batch must compact several times, results must
+    be identical with compaction switched off, and the stragglers (the moved slots) must match the oracle bit for bit."""
+    N, F, mi = 18432, 700, 40
+    lr = np.zeros((F, N))
+    # likelihood ratios per frame: most frames at eps 0.005, every 8th at 0.02 (never converges)
+    for f in range(F):
+        eps = 0.02 if f % 8 == 3 else 0.005
+        lr[f] = _bsc_lr(cws[f % 272], ol.bsc_flips(77, f, N, eps), 0.01)
+    want = ("bits", "iters", "ok", "post")
+    dec = ldpc.Decoder(code18432, wave_frames=512)
+    r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=want)
+    assert dec.stats()["compactions"] >= 2, dec.stats()
+    os.environ["DNALDPC_NO_COMPACT"] = "1"
+    try:
+        r0 = dec.decode(ldpc.IN_LR_F64, lr, mi, want=want)
+        assert dec.stats()["compactions"] == 0
+    finally:
+        del os.environ["DNALDPC_NO_COMPACT"]
+    dec.close()
+    for k in want:
+        assert np.array_equal(r[k].view(np.uint64) if k == "post" else r[k], r0[k].view(np.uint64) if k == "post" else r0[k]), k
+    assert (r["iters"] == mi).sum() >= F // 8 - 2 and (r["iters"] < 15).sum() > F // 2
+    for f in list(range(3, F, 40)) + list(range(0, F, 97)):
+        o = orc18432.decode(lr[f], mi)
+        assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"] and np.array_equal(r["bits"][f], o["dblk"]), f
+        assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
+
+
 def test_smem_check_kernel_mixed_groups_in_subprocess():
     """The shared-memory check kernel normally runs only in the steady state (full groups, nobody admitted). Its
     cp.async path for mixed groups (fresh / idle lanes) is forced here with the A/B switch, in a child process
