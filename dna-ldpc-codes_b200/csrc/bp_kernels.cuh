@@ -429,34 +429,103 @@ assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round,
 constexpr int kSynThreads = 256;
 constexpr int kSynSplit = 64;  // CTAs per group; the last one to arrive applies the loop control
 
-__global__ void __launch_bounds__(kSynThreads)
-syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t *__restrict__ iters_out,
-                       uint8_t *__restrict__ ok_out, const int32_t *__restrict__ row_ptr,
-                       const int32_t *__restrict__ col_idx, int M, int N, int g0, int max_iter, int consider_new, int fixed_iters,
-                       unsigned int *__restrict__ counter /* [0] += slots still busy (active or awaiting harvest) + pending
-                                                             frames, or NULL when a later launch of the tick counts */,
-                       unsigned int *__restrict__ finished /* += frames that finished in this launch */,
-                       unsigned int *__restrict__ counters_to_zero /* ring entry (3 words) re-armed for a later tick, or NULL */,
-                       int clear_fresh /* tick without admission: no assign_kernel will reset the fresh marks */,
-                       long long F) {
-    if (counters_to_zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        counters_to_zero[0] = 0; counters_to_zero[1] = 0; counters_to_zero[2] = 0;
+struct SynArgs {
+    int32_t *iters_out;
+    uint8_t *ok_out;
+    int M, N, g0, max_iter, consider_new, fixed_iters;
+    unsigned int *counter;          // [0] += slots still busy (active or awaiting harvest) + pending frames, or NULL when a
+                                    // later launch of the tick counts
+    unsigned int *finished;         // += frames that finished in this launch
+    unsigned int *counters_to_zero; // ring entry (3 words) re-armed for a later tick, or NULL
+    int clear_fresh;                // tick without admission: no assign_kernel will reset the fresh marks
+    long long F;
+};
+
+// Common head: housekeeping + "nothing to examine in this group" (uniform over the CTAs of the group: the masks only
+// change in the last arriver). Returns the mask of slots to examine (0 = this CTA is finished).
+__device__ __forceinline__ uint32_t syn_head(const SchedArrays &s, const SynArgs &a, int g, uint32_t &act) {
+    if (a.counters_to_zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        a.counters_to_zero[0] = 0; a.counters_to_zero[1] = 0; a.counters_to_zero[2] = 0;
     }
-    const int g = g0 + blockIdx.y;
-    const uint32_t act = s.actw[g];
-    const uint32_t consider = consider_new ? s.newfw[g] : act;
-    if (consider == 0) {  // uniform over the CTAs of the group: the masks only change in the last arriver
-        if (counter && blockIdx.x == 0 && threadIdx.x == 0) {
-            unsigned add = (unsigned)(__popc(act) + __popc(s.donew[g]));
-            if (blockIdx.y == 0) {
-                const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
-                if (nx < F) add += (unsigned)min(F - nx, 1000000000LL);
-            }
-            if (add) atomicAdd(counter, add);
+    act = s.actw[g];
+    const uint32_t consider = a.consider_new ? s.newfw[g] : act;
+    if (consider == 0 && a.counter && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned add = (unsigned)(__popc(act) + __popc(s.donew[g]));
+        if (blockIdx.y == 0) {
+            const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
+            if (nx < a.F) add += (unsigned)min(a.F - nx, 1000000000LL);
         }
-        return;
+        if (add) atomicAdd(a.counter, add);
     }
-    const uint32_t *dw = decw + (size_t)g * N;
+    return consider;
+}
+
+// Common tail: OR-reduce the CTA's parity words, publish them, and let the last CTA of the group to arrive apply the
+// per-slot loop control (dec.cpp:594-599).
+template <int THREADS>
+__device__ __forceinline__ void syn_tail(const SchedArrays &s, const SynArgs &a, int g, uint32_t act, uint32_t consider, uint32_t acc) {
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    __shared__ uint32_t s_or[THREADS / 32];
+    __shared__ unsigned int s_ticket;
+    if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t part = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) part |= s_or[w];
+        if (part) atomicOr(s.unsatw + g, part);
+        __threadfence();
+        s_ticket = atomicAdd(s.arrive + g, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    if (threadIdx.x < 32) {  // last CTA of the group: every partial OR is visible
+        __threadfence();
+        const uint32_t unsat = *((volatile uint32_t *)(s.unsatw + g));
+        const int f = threadIdx.x, slot = g * kFG + f;
+        const bool mine = (consider >> f) & 1u;
+        const int it = mine ? s.slot_iter[slot] : 0;
+        const uint32_t maxed = __ballot_sync(0xffffffffu, mine && it >= a.max_iter);
+        // fixed_iters (Run_Belief_Propagation_Decoder_SAVE, dec.cpp:192-223): a zero syndrome does not stop the frame
+        const uint32_t done = a.fixed_iters ? (consider & maxed) : ((consider & ~unsat) | (consider & maxed));
+        const uint32_t done_ok = done & ~unsat;
+        if ((done >> f) & 1u) {
+            const int fr = s.slot_frame[slot];
+            a.iters_out[fr] = it;
+            a.ok_out[fr] = (uint8_t)((done_ok >> f) & 1u);
+        } else if (mine) {
+            s.slot_iter[slot] = it + 1;  // this slot runs one more iteration now
+        }
+        if (f == 0) {
+            const uint32_t still = act & ~done;
+            const uint32_t dn = s.donew[g] | done;
+            s.actw[g] = still;
+            s.donew[g] = dn;
+            s.unsatw[g] = 0;  // re-armed
+            s.arrive[g] = 0;
+            if (a.clear_fresh) s.freshw[g] = 0;  // every slot admitted earlier has had its first check pass
+            if (done) atomicAdd(a.finished, (unsigned)__popc(done));
+            if (a.counter) {
+                unsigned add = (unsigned)(__popc(still) + __popc(dn));
+                if (blockIdx.y == 0) {
+                    const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
+                    if (nx < a.F) add += (unsigned)min(a.F - nx, 1000000000LL);
+                }
+                if (add) atomicAdd(a.counter, add);
+            }
+        }
+    }
+}
+
+// Variant 1 (any N): decision words gathered from global memory (L2), gridDim.x = kSynSplit CTAs per group.
+__global__ void __launch_bounds__(kSynThreads)
+syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, SynArgs a, const int32_t *__restrict__ row_ptr,
+                       const int32_t *__restrict__ col_idx) {
+    const int g = a.g0 + blockIdx.y, M = a.M;
+    uint32_t act;
+    const uint32_t consider = syn_head(s, a, g, act);
+    if (consider == 0) return;
+    const uint32_t *dw = decw + (size_t)g * a.N;
     // 8 lanes per check: their index loads are one coalesced run and all gathers of a check are in flight at once
     // (two dependent memory latencies per check instead of one per edge); XOR-folded over the 8 lanes with shuffles.
     const int sub = threadIdx.x & 7;
@@ -476,57 +545,49 @@ syndrome_update_kernel(const uint32_t *__restrict__ decw, SchedArrays s, int32_t
         p ^= __shfl_xor_sync(0xffffffffu, p, 4);
         acc |= p;
     }
-    acc = __reduce_or_sync(0xffffffffu, acc);
-    __shared__ uint32_t s_or[kSynThreads / 32];
-    __shared__ unsigned int s_ticket;
-    if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = acc;
+    syn_tail<kSynThreads>(s, a, g, act, consider, acc);
+}
+
+// Variant 2 (N decision words fit in shared memory): a CTA stages the group's N decision words in shared memory with
+// coalesced 16-byte loads and gathers from there. Each word is used by every check of its bit (8 for the n=18432
+// code), so the L2 -> SM traffic of variant 1 (one 32 B sector per 4-byte gather, ~600 MB per launch over 128 groups)
+// becomes one streamed copy of N words per CTA. gridDim.x = kSynSmemSplit CTAs per group, each taking a contiguous
+// range of checks.
+constexpr int kSynSmemThreads = 1024;
+constexpr int kSynSmemSplit = 2;
+
+__global__ void __launch_bounds__(kSynSmemThreads)
+syndrome_update_smem_kernel(const uint32_t *__restrict__ decw, SchedArrays s, SynArgs a, const int32_t *__restrict__ row_ptr,
+                            const int32_t *__restrict__ col_idx) {
+    extern __shared__ __align__(16) uint32_t sdw[];
+    const int g = a.g0 + blockIdx.y, M = a.M, N = a.N;
+    uint32_t act;
+    const uint32_t consider = syn_head(s, a, g, act);
+    if (consider == 0) return;
+    const uint32_t *dw = decw + (size_t)g * N;
+    const int n4 = N >> 2;  // the group's words start 16-byte aligned when N % 4 == 0 (checked by the host)
+    for (int q = threadIdx.x; q < n4; q += kSynSmemThreads) reinterpret_cast<uint4 *>(sdw)[q] = __ldg(reinterpret_cast<const uint4 *>(dw) + q);
+    for (int j = (n4 << 2) + threadIdx.x; j < N; j += kSynSmemThreads) sdw[j] = __ldg(dw + j);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t part = 0;
-#pragma unroll
-        for (int w = 0; w < kSynThreads / 32; w++) part |= s_or[w];
-        if (part) atomicOr(s.unsatw + g, part);
-        __threadfence();
-        s_ticket = atomicAdd(s.arrive + g, 1u);
-    }
-    __syncthreads();
-    if (s_ticket != kSynSplit - 1) return;
-    if (threadIdx.x < 32) {  // last CTA of the group: every partial OR is visible
-        __threadfence();
-        const uint32_t unsat = *((volatile uint32_t *)(s.unsatw + g));
-        const int f = threadIdx.x, slot = g * kFG + f;
-        const bool mine = (consider >> f) & 1u;
-        const int it = mine ? s.slot_iter[slot] : 0;
-        const uint32_t maxed = __ballot_sync(0xffffffffu, mine && it >= max_iter);
-        // fixed_iters (Run_Belief_Propagation_Decoder_SAVE, dec.cpp:192-223): a zero syndrome does not stop the frame
-        const uint32_t done = fixed_iters ? (consider & maxed) : ((consider & ~unsat) | (consider & maxed));
-        const uint32_t done_ok = done & ~unsat;
-        if ((done >> f) & 1u) {
-            const int fr = s.slot_frame[slot];
-            iters_out[fr] = it;
-            ok_out[fr] = (uint8_t)((done_ok >> f) & 1u);
-        } else if (mine) {
-            s.slot_iter[slot] = it + 1;  // this slot runs one more iteration now
+    const int sub = threadIdx.x & 7;
+    const int rows_per_iter = kSynSmemThreads / 8;
+    const int per_cta = (M + gridDim.x - 1) / gridDim.x;
+    const int i_beg = blockIdx.x * per_cta, i_end = min(M, i_beg + per_cta);
+    uint32_t acc = 0;
+    for (int ib = i_beg; ib < i_end; ib += rows_per_iter) {  // warp-uniform trip count
+        const int i = ib + (threadIdx.x >> 3);
+        uint32_t p = 0;
+        if (i < i_end) {
+            const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
+#pragma unroll 4
+            for (int e = e0 + sub; e < e1; e += 8) p ^= sdw[__ldg(col_idx + e)];
         }
-        if (f == 0) {
-            const uint32_t still = act & ~done;
-            const uint32_t dn = s.donew[g] | done;
-            s.actw[g] = still;
-            s.donew[g] = dn;
-            s.unsatw[g] = 0;  // re-armed
-            s.arrive[g] = 0;
-            if (clear_fresh) s.freshw[g] = 0;  // every slot admitted earlier has had its first check pass
-            if (done) atomicAdd(finished, (unsigned)__popc(done));
-            if (counter) {
-                unsigned add = (unsigned)(__popc(still) + __popc(dn));
-                if (blockIdx.y == 0) {
-                    const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
-                    if (nx < F) add += (unsigned)min(F - nx, 1000000000LL);
-                }
-                if (add) atomicAdd(counter, add);
-            }
-        }
+        p ^= __shfl_xor_sync(0xffffffffu, p, 1);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 2);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 4);
+        acc |= p;
     }
+    syn_tail<kSynSmemThreads>(s, a, g, act, consider, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -573,80 +634,94 @@ template <int KIND> __device__ __forceinline__ double load_llr(const SetupArgs &
     return a.table[(int)((const int8_t *)row)[j] + 128];
 }
 
-constexpr int kHsTiles = 16;  // 32-bit tiles per CTA: keeps the (usually idle) launch down to a few thousand CTAs
+// One warp per 32-bit x 32-slot tile, no block-level synchronisation: the tiles of a group are independent, so the
+// warps of a CTA (each with a private transpose buffer) overlap each other's memory latencies.
+constexpr int kHsWarps = 4;         // warps per CTA
+constexpr int kHsTilesPerWarp = 2;  // tiles a warp walks through
 
 template <typename T, int KIND, int ALG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kHsWarps * 32)
 harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ lratio, const T *__restrict__ post,
                      uint32_t *__restrict__ decw, int N, int g0) {
     const int g = g0 + blockIdx.y;
     const uint32_t hv = s.harvw[g], nf = s.newfw[g];
     if ((hv | nf) == 0) return;
-    __shared__ double tile[32][33];
-    __shared__ int s_new[32], s_old[32], s_oldit[32];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (ty == 0) {
-        s_new[tx] = s.slot_frame[g * kFG + tx];
-        s_old[tx] = s.harv_frame[g * kFG + tx];
-        s_oldit[tx] = s.harv_iter[g * kFG + tx];
-    }
-    __syncthreads();
+    __shared__ double tiles[kHsWarps][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*tile)[33] = tiles[warp];
+    const int my_new = s.slot_frame[g * kFG + lane];   // lane = slot
+    const int my_old = s.harv_frame[g * kFG + lane];
+    const int my_oldit = s.harv_iter[g * kFG + lane];
+    const bool is_new = (nf >> lane) & 1u, is_old = (hv >> lane) & 1u;
     const int ntiles = (N + 31) / 32;
-    for (int tile_id = blockIdx.x * kHsTiles; tile_id < min(ntiles, (int)(blockIdx.x + 1) * kHsTiles); tile_id++) {
+    const int t0 = (blockIdx.x * kHsWarps + warp) * kHsTilesPerWarp;
+    for (int tile_id = t0; tile_id < min(ntiles, t0 + kHsTilesPerWarp); tile_id++) {
         const int j0 = tile_id * 32;
+        const int j = j0 + lane;                                              // lane = bit of the tile
+        uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;               // decisions of bit j, one bit per slot
         if (hv) {
-            const int j = j0 + tx;
-            const uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;  // tx = bit of the tile
-            if (h.bits && ty == 0) {
+            if (h.bits) {  // 32 x 32 bit transpose by ballots: slot f ends up with the word of its frame
+                uint32_t mine = 0;
                 for (uint32_t m = hv; m; m &= m - 1) {
                     const int f = __ffs(m) - 1;
                     const uint32_t b = __ballot_sync(0xffffffffu, (word >> f) & 1u);
-                    if (tx == 0) h.bits[(size_t)s_old[f] * h.wpf + tile_id] = b;
+                    if (lane == f) mine = b;
                 }
+                if (is_old) h.bits[(size_t)my_old * h.wpf + tile_id] = mine;
             }
-            if (h.dblk && j < N) {
-                for (int r = ty; r < 32; r += 8)
-                    if ((hv >> r) & 1u) h.dblk[(size_t)s_old[r] * N + j] = (uint8_t)((word >> r) & 1u);
+            if (h.dblk) {
+                for (uint32_t m = hv; m; m &= m - 1) {
+                    const int f = __ffs(m) - 1;
+                    const int fr = __shfl_sync(0xffffffffu, my_old, f);
+                    if (j < N) h.dblk[(size_t)fr * N + j] = (uint8_t)((word >> f) & 1u);
+                }
             }
             if (h.posterior) {
-                for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
+                for (int r = 0; r < 32; r++) {  // r = bit of the tile, lane = slot
                     const int jj = j0 + r;
                     double v = 0;
-                    if (jj < N && ((hv >> tx) & 1u)) {
-                        const size_t idx = ((size_t)g * N + jj) * kFG + tx;
-                        v = s_oldit[tx] > 0 ? (double)post[idx] : (double)lratio[idx];
+                    if (jj < N && is_old) {
+                        const size_t idx = ((size_t)g * N + jj) * kFG + lane;
+                        v = my_oldit > 0 ? (double)post[idx] : (double)lratio[idx];
                     }
-                    tile[r][tx] = v;
+                    tile[r][lane] = v;
                 }
-                __syncthreads();
-                if (j < N)
-                    for (int r = ty; r < 32; r += 8)  // r = slot, tx = bit
-                        if ((hv >> r) & 1u) h.posterior[(size_t)s_old[r] * N + j] = tile[tx][r];
+                __syncwarp();
+                for (uint32_t m = hv; m; m &= m - 1) {  // lane = bit
+                    const int f = __ffs(m) - 1;
+                    const int fr = __shfl_sync(0xffffffffu, my_old, f);
+                    if (j < N) h.posterior[(size_t)fr * N + j] = tile[lane][f];
+                }
+                __syncwarp();  // the old lratio / decw values have been read: the tile may be overwritten
             }
-            __syncthreads();  // the old lratio / decw values have been read: the tile may be overwritten
         }
         if (nf) {
-            for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit of the tile
-                const int j = j0 + tx;
-                double v = 1.0;
-                if (((nf >> r) & 1u) && j < N) v = ALG == ALG_MINSUM ? load_llr<KIND>(a, s_new[r], j) : load_lr<KIND>(a, s_new[r], j);
-                tile[r][tx] = v;
+            uint32_t bsc_word = 0;
+            if (KIND == IN_BSC_BITS) {  // no transpose needed: slot `lane` holds the 32 received bits of its frame's tile
+                if (is_new) bsc_word = ((const uint32_t *)((const char *)a.data + (size_t)my_new * a.frame_stride))[tile_id];
+            } else {
+                for (uint32_t m = nf; m; m &= m - 1) {  // r = slot, lane = bit of the tile: coalesced read of the frame's row
+                    const int r = __ffs(m) - 1;
+                    const int fr = __shfl_sync(0xffffffffu, my_new, r);
+                    double v = 1.0;
+                    if (j < N) v = ALG == ALG_MINSUM ? load_llr<KIND>(a, fr, j) : load_lr<KIND>(a, fr, j);
+                    tile[r][lane] = v;
+                }
+                __syncwarp();
             }
-            __syncthreads();
-            for (int r = ty; r < 32; r += 8) {  // r = bit of the tile, tx = slot
-                const int j = j0 + r;
-                const T v = ALG == ALG_MINSUM ? (T)tile[tx][r] : clamp_lr((T)tile[tx][r]);
+            uint32_t wmine = 0;
+            for (int r = 0; r < 32; r++) {  // r = bit of the tile, lane = slot
+                const int jj = j0 + r;
+                double dv = 1.0;
+                if (is_new) dv = KIND == IN_BSC_BITS ? a.table[(bsc_word >> r) & 1u] : tile[lane][r];
+                const T v = ALG == ALG_MINSUM ? (T)dv : clamp_lr((T)dv);
                 // initial decision: BP lratio < 1 (dec.cpp:626); min-sum !(LLR > 0) (Init_MSA_INF, dec.cpp:1311-1312)
                 const uint32_t w = __ballot_sync(0xffffffffu, ALG == ALG_MINSUM ? !(v > T(0)) : (v < T(1)));
-                if (j < N) {
-                    if ((nf >> tx) & 1u) lratio[((size_t)g * N + j) * kFG + tx] = v;
-                    if (tx == 0) {
-                        uint32_t *dst = decw + (size_t)g * N + j;
-                        *dst = (*dst & ~nf) | (w & nf);
-                    }
-                }
+                if (lane == r) wmine = w;
+                if (jj < N && is_new) lratio[((size_t)g * N + jj) * kFG + lane] = v;
             }
-            __syncthreads();  // before the next tile reuses the shared buffer
+            if (j < N) decw[(size_t)g * N + j] = (word & ~nf) | (wmine & nf);
+            __syncwarp();  // before the next tile reuses the transpose buffer
         }
     }
 }

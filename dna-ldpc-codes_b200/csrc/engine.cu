@@ -185,6 +185,31 @@ template <typename T> int Engine::launch_col(int g0, int G, bool want_post, cuda
     return DNALDPC_OK;
 }
 
+// check() + loop control for the slots under consideration (syndrome_update_*_kernel)
+int Engine::launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int consider_new, int fixed, unsigned *counter,
+                            unsigned *finished, unsigned *rearm, int clear_fresh, int64_t F, cudaStream_t st) {
+    SchedArrays s;
+    fill_sched(s);
+    SynArgs a;
+    a.iters_out = out.iters; a.ok_out = out.is_codeword;
+    a.M = M_; a.N = N_; a.g0 = 0; a.max_iter = max_iter; a.consider_new = consider_new; a.fixed_iters = fixed;
+    a.counter = counter; a.finished = finished; a.counters_to_zero = rearm; a.clear_fresh = clear_fresh; a.F = (long long)F;
+    const size_t smem = (size_t)N_ * sizeof(uint32_t);
+    static const bool no_smem = getenv("DNALDPC_SYN_GATHER") != nullptr;  // A/B switch: global-gather variant
+    if (!no_smem && smem <= 96 * 1024 && N_ % 4 == 0) {  // the group's decision words staged in shared memory
+        if (!syn_attr_set_) {
+            CK(cudaFuncSetAttribute(syndrome_update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            syn_attr_set_ = true;
+        }
+        syndrome_update_smem_kernel<<<dim3(kSynSmemSplit, (unsigned)G), kSynSmemThreads, smem, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
+    } else {
+        syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
+    }
+    stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return DNALDPC_OK;
+}
+
 template <typename T>
 int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &out, int g0, int G, cudaStream_t st) {
     SetupArgs a;
@@ -202,13 +227,14 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
         syndrome_bytes_kernel<<<grid, 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, M_, N_, g0, out.pchk);
         stats.kernel_launches++;
     }
-    dim3 grid((unsigned)(((N_ + 31) / 32 + kHsTiles - 1) / kHsTiles), (unsigned)G);
+    constexpr int tiles_per_cta = kHsWarps * kHsTilesPerWarp;
+    dim3 grid((unsigned)(((N_ + 31) / 32 + tiles_per_cta - 1) / tiles_per_cta), (unsigned)G);
     T *lr = (T *)d_lratio_;
     const T *post = (const T *)d_post_;
 #define HS(K)                                                                                                   \
     do {                                                                                                        \
-        if (minsum_) harvest_setup_kernel<T, K, ALG_MINSUM><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0); \
-        else harvest_setup_kernel<T, K, ALG_BP><<<grid, 256, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0);         \
+        if (minsum_) harvest_setup_kernel<T, K, ALG_MINSUM><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0); \
+        else harvest_setup_kernel<T, K, ALG_BP><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0);         \
     } while (0)
     switch (in.kind) {
         case DNALDPC_IN_LR_F64: HS(IN_LR_F64); break;
@@ -296,18 +322,13 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
                 stats.kernel_launches++;
                 rc = launch_harvest_setup<T>(in, out, 0, G, st);
                 if (rc) return rc;
-                syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(
-                    d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, round == 2, fixed,
-                    round == 2 ? cnt : nullptr, cnt + 2, round == 1 ? rearm : nullptr, 0, (long long)F);
-                stats.kernel_launches++;
-                CK(cudaGetLastError());
+                rc = launch_syndrome(out, G, max_iter, round == 2, fixed, round == 2 ? cnt : nullptr, cnt + 2,
+                                     round == 1 ? rearm : nullptr, 0, F, st);
+                if (rc) return rc;
             }
         } else {
-            syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(
-                d_decw_, s, out.iters, out.is_codeword, d_row_ptr_, d_col_idx_, M_, N_, 0, max_iter, 0, fixed, cnt, cnt + 2,
-                rearm, 1, (long long)F);
-            stats.kernel_launches++;
-            CK(cudaGetLastError());
+            rc = launch_syndrome(out, G, max_iter, 0, fixed, cnt, cnt + 2, rearm, 1, F, st);
+            if (rc) return rc;
         }
         CK(cudaMemcpyAsync(h_counters_ + 3 * (tick % kRing), cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev_[tick % kRing], st));

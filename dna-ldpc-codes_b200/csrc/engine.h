@@ -40,6 +40,8 @@ class Engine {
     template <typename T> int launch_row(int g0, int G, cudaStream_t st);
     template <typename T> int launch_col(int g0, int G, bool want_post, cudaStream_t st);
     template <typename T> int launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &out, int g0, int G, cudaStream_t st);
+    int launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int consider_new, int fixed, unsigned *counter,
+                        unsigned *finished, unsigned *rearm, int clear_fresh, int64_t F, cudaStream_t st);
     int ensure_slots(int groups, bool want_post);
     int ensure_frame_scratch(int64_t F);
     int fail(cudaError_t e, const char *what);
@@ -51,7 +53,7 @@ class Engine {
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
-    bool smem_attr_set_[2] = {false, false};
+    bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false;
     bool steady_ = false;  // last polled tick: all slots busy, no frame admitted
     bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
