@@ -335,6 +335,122 @@ int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char
     return n;
 }
 
+
+/* ---------- sliding-window BP for spatially-coupled codes ------------------------------------------- */
+
+/* Schedule of Run_SW_Decoder (dec.cpp:2092-2196): the window ranges of every position t = 0..L-1, computed with the
+ * reference's own running sums. sched[t] = {V_Start, V_End, C_Start, C_End, V_Check_End, C_Check_End, Init_from, Init_to}
+ * (Init_from == Init_to: no Init_SW_Decoder call at that position). */
+void orc_sw_schedule(int M, int N, int code_type, int L, int w, int win, const int *Mv, const int *Mc, int *sched) {
+    int D = code_type == 0 ? L + w - 1 : L + (w - 1) / 2;                                   /* dec.cpp:2115-2119 */
+    int V_Start = 0, V_End = 0, C_Start = 0, C_End = 0, V_Check_End = 0, C_Check_End = 0;
+    for (int i = 0; i < w; i++) { V_Check_End += Mv[i]; C_Check_End += Mc[i]; }              /* :2128-2132 */
+    for (int i = 0; i < win; i++) { V_End += Mv[i]; C_End += Mc[i]; }                        /* :2134-2138 */
+    int *r = sched;
+    r[0] = V_Start; r[1] = V_End; r[2] = C_Start; r[3] = C_End; r[4] = V_Check_End; r[5] = C_Check_End;
+    r[6] = V_Start; r[7] = V_End;                                                            /* :2144 */
+    for (int t = 1; t < L; t++) {                                                            /* :2150-2183 */
+        V_Start += Mv[t - 1];
+        C_Start += Mc[t - 1];
+        if (t + win >= L) V_End = N; else V_End += Mv[t + win - 1];
+        if (t + win >= D) C_End = M; else C_End += Mc[t + win - 1];
+        if (t + w >= L) { V_Check_End = N; C_Check_End = M; }
+        else { V_Check_End += Mv[t + w - 1]; C_Check_End += Mc[t + w - 1]; }
+        r = sched + 8 * t;
+        r[0] = V_Start; r[1] = V_End; r[2] = C_Start; r[3] = C_End; r[4] = V_Check_End; r[5] = C_Check_End;
+        r[6] = r[7] = V_End;
+        if (t + win <= L) r[6] = V_End - Mv[t + win - 1];                                    /* :2176-2180 */
+    }
+}
+
+/* Run_SW_Decoder (dec.cpp:2092-2196) with Init_SW_Decoder (2366-2386), Iter_SW_Decoder (2388-2432), Check_Update_SW
+ * (2478-2500), Variable_Update_SW (2502-2548), Decision_SW (2630-2645) and check_bound (check.cpp:49-72) ->
+ * mod2sparse_mulvec_bound (mod2sparse.cpp:883-912). Messages start at 0 (alloc_entry, mod2sparse.cpp:61-62); unlike
+ * the flooding decoder both e->pr and e->lr are live at the same time (a bit that has left the window keeps its pr).
+ * dblk[N] is in/out: bits outside every window so far keep the caller's value and count as set when non-zero (the
+ * reference passes a buffer filled with 2, DNA_main.cpp:664-666). Every position runs at least one update; the
+ * per-position count n is that of Iter_SW_Decoder (updates - 1). Returns floor(sum of n / L) like the reference;
+ * iters_pos (may be NULL) receives the L per-position counts. position_BER (test_BER) is a diagnostic and not produced. */
+int orc_sw_decode(const orc_code *c, const double *lratio, int max_iter, int code_type, int L, int w, int win,
+                  const int *Mv, const int *Mc, char *dblk, char *pchk, int *is_codeword, int *iters_pos,
+                  double *msg_pr, double *msg_lr) {
+    size_t E = (size_t)(c->E > 0 ? c->E : 1);
+    double *pr = (double *)calloc(E, sizeof(double)), *lr = (double *)calloc(E, sizeof(double));
+    int *erow = (int *)malloc(sizeof(int) * E);
+    for (int i = 0; i < c->M; i++)
+        for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) erow[e] = i;
+    int *sched = (int *)malloc(sizeof(int) * 8 * (size_t)(L > 0 ? L : 1));
+    orc_sw_schedule(c->M, c->N, code_type, L, w, win, Mv, Mc, sched);
+    double sum = 0;
+    for (int t = 0; t < L; t++) {
+        const int *r = sched + 8 * t;
+        const int V0 = r[0], V1 = r[1], C0 = r[2], C1 = r[3], VC = r[4], CC = r[5];
+        for (int j = r[6]; j < r[7]; j++)                                 /* Init_SW_Decoder */
+            for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) { pr[c->col_edge[k]] = lratio[j]; lr[c->col_edge[k]] = 1; }
+        int n;
+        for (n = 0;; n++) {                                               /* Iter_SW_Decoder */
+            for (int i = C0; i < C1; i++) {                               /* Check_Update_SW: the whole row */
+                double dl = 1;
+                for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) { lr[e] = dl; dl *= 1 - 2 / (1 + pr[e]); }
+                dl = 1;
+                for (int e = c->row_ptr[i + 1] - 1; e >= c->row_ptr[i]; e--) {
+                    double tt = lr[e] * dl;
+                    lr[e] = (1 + tt) / (1 - tt);
+                    dl *= 1 - 2 / (1 + pr[e]);
+                }
+            }
+            for (int j = V0; j < V1; j++) {                               /* Variable_Update_SW: rows of the window only */
+                double p = lratio[j];
+                for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) {
+                    int e = c->col_edge[k];
+                    if (erow[e] < C1 && erow[e] >= C0) { pr[e] = p; p *= lr[e]; }
+                }
+                p = 1;  /* (the isnan test on the forward product is dead: it is overwritten here, dec.cpp:2522-2527) */
+                for (int k = c->col_ptr[j + 1] - 1; k >= c->col_ptr[j]; k--) {
+                    int e = c->col_edge[k];  /* entries with row >= C1 are skipped either way (dec.cpp:2528-2532) */
+                    if (erow[e] < C1 && erow[e] >= C0) {
+                        pr[e] *= p;
+                        if (isnan(pr[e])) pr[e] = 1;
+                        p *= lr[e];
+                    }
+                }
+            }
+            for (int j = V0; j < V1; j++) {                               /* Decision_SW: no NaN guard, NaN -> 0 */
+                double p = lratio[j];
+                for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) {
+                    int e = c->col_edge[k];
+                    if (erow[e] < C1 && erow[e] >= C0) p *= lr[e];
+                }
+                dblk[j] = (p <= 1);
+            }
+            int cw = 0;                                                   /* check_bound */
+            for (int i = C0; i < CC; i++) pchk[i] = 0;
+            for (int j = V0; j < VC; j++)
+                if (dblk[j])
+                    for (int k = c->col_ptr[j]; k < c->col_ptr[j + 1]; k++) {
+                        int e = c->col_edge[k];
+                        if (erow[e] < CC && erow[e] >= C0) pchk[erow[e]] ^= 1;
+                    }
+            for (int i = C0; i < CC; i++) cw += pchk[i];
+            if (n == max_iter || cw == 0) break;
+        }
+        if (iters_pos) iters_pos[t] = n;
+        sum += n;
+    }
+    int wgt = 0;                                                          /* check(): mod2sparse_mulvec tests u[j] != 0 */
+    for (int i = 0; i < c->M; i++) {
+        int p = 0;
+        for (int e = c->row_ptr[i]; e < c->row_ptr[i + 1]; e++) p ^= (dblk[c->col_idx[e]] != 0);
+        pchk[i] = (char)p;
+        wgt += p;
+    }
+    if (is_codeword) *is_codeword = (wgt == 0);
+    if (msg_pr) memcpy(msg_pr, pr, sizeof(double) * (size_t)c->E);
+    if (msg_lr) memcpy(msg_lr, lr, sizeof(double) * (size_t)c->E);
+    free(pr); free(lr); free(erow); free(sched);
+    return (int)floor(sum / L);                                           /* dec.cpp:2193-2194 */
+}
+
 /* ---------- likelihood setup --------------------------------------------------------------- */
 
 void orc_lr_from_llr(const double *llr, int n, double *lr) { /* DNA_main.cpp:1342-1344 */

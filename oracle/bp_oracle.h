@@ -60,6 +60,12 @@ int orc_bp_decode_f32(const orc_code *c, const float *lratio, int max_iter, char
 long orc_bp_decode_many(const orc_code *c, const double *lratio, int F, int max_iter, char *dblk,
                         int *iters, int *is_codeword);
 
+/* Sliding-window BP for spatially-coupled codes: Run_SW_Decoder (dec.cpp:2092-2196); see bp_oracle.c. sched: [L][8]. */
+void orc_sw_schedule(int M, int N, int code_type, int L, int w, int win, const int *Mv, const int *Mc, int *sched);
+int orc_sw_decode(const orc_code *c, const double *lratio, int max_iter, int code_type, int L, int w, int win,
+                  const int *Mv, const int *Mc, char *dblk, char *pchk, int *is_codeword, int *iters_pos,
+                  double *msg_pr, double *msg_lr);
+
 /* Likelihood setup.
  * orc_lr_from_llr : LR = exp(LLR)                         (DNA_main.cpp:1342-1344)
  * orc_std_dev     : sigma = 1/sqrt(2*R*10^(EbNo/10))      (channel.cpp:9-16)

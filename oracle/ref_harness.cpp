@@ -91,6 +91,35 @@ int ref_decode_minsum(const double *llr, int maxit, char *dblk, char *pchk, int 
     return n;
 }
 
+/* Sliding-window BP for spatially-coupled codes, Run_SW_Decoder (dec.cpp:2092-2196), code_type 0 = two-sided termination.
+ * dblk is in/out like in the reference: LDPC_Decode hands it g_bit_stream_trans, which Alloc_Mem fills with 2
+ * (DNA_main.cpp:664-666); callers of this harness do the same. position_BER is the reference's per-position
+ * diagnostic (test_BER, dec.cpp:225-239); allocated here like Alloc_Mem does and discarded.
+ * msgs_pr / msgs_lr (optional, E doubles each, CSR order): final e->pr / e->lr. */
+int ref_decode_sw(const double *lratio, int maxit, int code_type, int L, int w, int win, const int *Mv, const int *Mc,
+                  char *dblk, char *pchk, int *is_codeword, double *msgs_pr, double *msgs_lr) {
+    max_iter = maxit;
+    int flag = 0;
+    double **pber = (double **)calloc(200, sizeof(double *));
+    for (int i = 0; i < 200; i++) pber[i] = (double *)calloc(L + 1, sizeof(double));
+    /* fresh message state, as after read_pchk in a new process (entries come from calloc: pr = lr = 0) */
+    for (int i = 0; i < M; i++)
+        for (mod2entry *p = mod2sparse_first_in_row(H, i); !mod2sparse_at_end(p); p = mod2sparse_next_in_row(p)) { p->pr = 0; p->lr = 0; }
+    int n = Run_SW_Decoder(H, (double *)lratio, dblk, pchk, &flag, pber, code_type, L, w, win, (int *)Mv, (int *)Mc);
+    for (int i = 0; i < 200; i++) free(pber[i]);
+    free(pber);
+    if (is_codeword) *is_codeword = flag;
+    if (msgs_pr || msgs_lr) {
+        int e = 0;
+        for (int i = 0; i < M; i++)
+            for (mod2entry *p = mod2sparse_first_in_row(H, i); !mod2sparse_at_end(p); p = mod2sparse_next_in_row(p), e++) {
+                if (msgs_pr) msgs_pr[e] = p->pr;
+                if (msgs_lr) msgs_lr[e] = p->lr;
+            }
+    }
+    return n;
+}
+
 /* check() alone (check.cpp:28-47). */
 int ref_check(const char *dblk, char *pchk) { return check(H, (char *)dblk, pchk); }
 

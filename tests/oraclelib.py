@@ -58,6 +58,9 @@ class Oracle:
             L.orc_bp_decode_fixed.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int)]
             L.orc_minsum_decode.argtypes = [C.POINTER(_Code), _dp, C.c_int, _cp, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
             L.orc_bp_decode_f32.argtypes = [C.POINTER(_Code), _fp, C.c_int, _cp, C.POINTER(C.c_int)]
+            L.orc_sw_schedule.argtypes = [C.c_int] * 6 + [_ip, _ip, _ip]
+            L.orc_sw_decode.argtypes = [C.POINTER(_Code), _dp] + [C.c_int] * 5 + [_ip, _ip, _cp, _cp, C.POINTER(C.c_int),
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
             L.orc_bp_decode_many.restype = C.c_long
             L.orc_bp_decode_many.argtypes = [C.POINTER(_Code), _dp, C.c_int, C.c_int, _cp, _ip, _ip]
             L.orc_std_dev.restype = C.c_double
@@ -150,6 +153,27 @@ class Oracle:
         n = self.lib().orc_minsum_decode(self._c, llr, max_iter, dblk, pchk.ctypes.data, C.byref(ok), L.ctypes.data)
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=L)
 
+    def decode_sw(self, lratio, max_iter, L, w, win, Mv, Mc, code_type=0, want_msgs=False, dblk_init=2):
+        """Run_SW_Decoder restated (sliding-window BP, SC-LDPC codes). dblk starts filled with `dblk_init` like the
+        reference's g_bit_stream_trans (DNA_main.cpp:664-666). -> dict(n, ok, dblk, pchk, iters_pos[L], pr/lr)"""
+        lratio = np.ascontiguousarray(lratio, dtype=np.float64)
+        Mv = np.ascontiguousarray(Mv, dtype=np.int32); Mc = np.ascontiguousarray(Mc, dtype=np.int32)
+        dblk = np.full(self.N, dblk_init, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        ip = np.zeros(L, dtype=np.int32)
+        pr = np.zeros(self.E, dtype=np.float64) if want_msgs else None
+        lr = np.zeros(self.E, dtype=np.float64) if want_msgs else None
+        ok = C.c_int(0)
+        n = self.lib().orc_sw_decode(self._c, lratio, max_iter, code_type, L, w, win, Mv, Mc, dblk, pchk, C.byref(ok),
+                                     ip.ctypes.data, pr.ctypes.data if want_msgs else None, lr.ctypes.data if want_msgs else None)
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, iters_pos=ip, pr=pr, lr=lr)
+
+    def sw_schedule(self, L, w, win, Mv, Mc, code_type=0):
+        Mv = np.ascontiguousarray(Mv, dtype=np.int32); Mc = np.ascontiguousarray(Mc, dtype=np.int32)
+        sched = np.zeros((L, 8), dtype=np.int32)
+        self.lib().orc_sw_schedule(self.M, self.N, code_type, L, w, win, Mv, Mc, sched.reshape(-1))
+        return sched
+
     def decode_f32(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float32)
         dblk = np.zeros(self.N, dtype=np.int8)
@@ -216,6 +240,7 @@ class RefLib:
             L.ref_check.argtypes = [_cp, _cp]
             L.ref_decode_fixed.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int)]
             L.ref_decode_minsum.argtypes = [_dp, C.c_int, _cp, _cp, C.POINTER(C.c_int), _dp]
+            L.ref_decode_sw.argtypes = [_dp] + [C.c_int] * 5 + [_ip, _ip, _cp, _cp, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
             L.ref_decode_many.restype = C.c_long
             L.ref_decode_many.argtypes = [_dp, C.c_int, C.c_int, _cp, _ip, _ip]
             cls._lib = L
@@ -275,6 +300,19 @@ class RefLib:
         ok = C.c_int(0)
         n = self._lib.ref_decode_minsum(llr, max_iter, dblk, pchk, C.byref(ok), L)
         return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, post=L)
+
+    def decode_sw(self, lratio, max_iter, L, w, win, Mv, Mc, code_type=0, want_msgs=False, dblk_init=2):
+        """The reference's Run_SW_Decoder (dec.cpp:2092-2196); dblk pre-filled with 2 like Alloc_Mem does."""
+        lratio = np.ascontiguousarray(lratio, dtype=np.float64)
+        Mv = np.ascontiguousarray(Mv, dtype=np.int32); Mc = np.ascontiguousarray(Mc, dtype=np.int32)
+        dblk = np.full(self.N, dblk_init, dtype=np.int8)
+        pchk = np.zeros(self.M, dtype=np.int8)
+        pr = np.zeros(self.E, dtype=np.float64) if want_msgs else None
+        lr = np.zeros(self.E, dtype=np.float64) if want_msgs else None
+        ok = C.c_int(0)
+        n = self._lib.ref_decode_sw(lratio, max_iter, code_type, L, w, win, Mv, Mc, dblk, pchk, C.byref(ok),
+                                    pr.ctypes.data if want_msgs else None, lr.ctypes.data if want_msgs else None)
+        return dict(n=n, ok=ok.value, dblk=dblk, pchk=pchk, pr=pr, lr=lr)
 
     def decode_many(self, lratio, max_iter):
         lratio = np.ascontiguousarray(lratio, dtype=np.float64)

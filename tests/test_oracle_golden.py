@@ -91,3 +91,23 @@ def test_rng_twin():
     for b, x in zip(bits, v):
         assert L.orc_rng_u64(7, 123, int(b), 2) == int(x)
     assert abs(ol.bsc_flips(7, 3, 18432, 0.02).mean() - 0.02) < 0.004
+
+
+def test_golden_sliding_window():
+    """Sliding-window BP: orc_sw_decode against vectors produced by the unmodified reference's
+    Run_SW_Decoder (dec.cpp:2092-2196) on the generated SC-LDPC code (tools/make_golden_sw.py)."""
+    import gen_sc_pchk
+    g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
+    path = os.path.join(ol.GOLDEN, "sc_z32_l12.pchk")
+    M, N, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(32, 12, 11)  # the generator still produces the committed file
+    orc = ol.Oracle(path)
+    assert (orc.M, orc.N) == (M, N) and np.array_equal(orc.row_ptr, row_ptr) and np.array_equal(orc.col_idx, col_idx)
+    assert np.array_equal(Mv, g["Mv"]) and np.array_equal(Mc, g["Mc"])
+    L, w = int(g["L"]), int(g["w"])
+    for name in g["names"]:
+        name = str(name)
+        r = orc.decode_sw(g[name + ".lratio"], int(g[name + ".max_iter"]), L, w, int(g[name + ".win"]), Mv, Mc, want_msgs=True)
+        assert r["n"] == int(g[name + ".n"]) and r["ok"] == int(g[name + ".ok"]), name
+        assert np.array_equal(np.packbits(r["dblk"].astype(np.uint8), bitorder="little"), g[name + ".dblk"]), name
+        assert np.array_equal(np.packbits(r["pchk"].astype(np.uint8), bitorder="little"), g[name + ".pchk"]), name
+        assert np.array_equal(_sha(r["pr"]), g[name + ".pr_sha"]) and np.array_equal(_sha(r["lr"]), g[name + ".lr_sha"]), name

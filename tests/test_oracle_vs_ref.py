@@ -87,3 +87,39 @@ def test_minsum_variant(pair):
         assert a["n"] == b["n"] and a["ok"] == b["ok"]
         assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"])
         assert np.array_equal(a["post"].view(np.uint64), b["post"].view(np.uint64))
+
+
+def test_sliding_window_variant_in_subprocess():
+    """orc_sw_decode vs the reference's Run_SW_Decoder (dec.cpp:2092-2196) on fresh seeded inputs, every final message
+    included. Child process: the reference object holds one .pchk per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.getcwd(), "tests")); sys.path.insert(0, os.path.join(os.getcwd(), "tools"))
+import oraclelib as ol, gen_sc_pchk
+path = os.path.join(ol.GOLDEN, "sc_z32_l12.pchk")
+M, N, rp, ci, Mv, Mc = gen_sc_pchk.gen_sc(32, 12, 11)
+ref, orc = ol.RefLib(path), ol.Oracle(path)
+rs = np.random.RandomState(99)
+iters = set()
+for t in range(24):
+    eps = [0.03, 0.05, 0.065, 0.08][t % 4]
+    win = [3, 4, 6, 12][(t // 4) % 4]
+    mi = [1, 8, 25][t % 3]
+    llr = np.where(rs.rand(N) < eps, -1.0, 1.0) * rs.uniform(1.0, 4.0, N)
+    llr[rs.rand(N) < 0.02] = 0.0
+    lr = np.exp(llr)
+    a = ref.decode_sw(lr, mi, 12, 3, win, Mv, Mc, want_msgs=True)
+    b = orc.decode_sw(lr, mi, 12, 3, win, Mv, Mc, want_msgs=True)
+    assert a["n"] == b["n"] and a["ok"] == b["ok"], t
+    assert np.array_equal(a["dblk"], b["dblk"]) and np.array_equal(a["pchk"], b["pchk"]), t
+    assert np.array_equal(a["pr"].view(np.uint64), b["pr"].view(np.uint64)) and np.array_equal(a["lr"].view(np.uint64), b["lr"].view(np.uint64)), t
+    iters.add(a["n"])
+print("ok", sorted(iters))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.startswith("ok"), res.stdout + res.stderr
