@@ -25,7 +25,7 @@ EXPORTS = [
     "dnaldpc_code_check_regular", "dnaldpc_decoder_create", "dnaldpc_decoder_destroy", "dnaldpc_decode_batch",
     "dnaldpc_decode_batch_device", "dnaldpc_run_bp_decoder", "dnaldpc_std_dev", "dnaldpc_vote_table",
     "dnaldpc_bsc_table", "dnaldpc_synth_bsc_device", "dnaldpc_get_stats", "dnaldpc_set_profiling",
-    "dnaldpc_selftest_math", "dnaldpc_redecode_sweep", "dnaldpc_get_trace",
+    "dnaldpc_selftest_math", "dnaldpc_redecode_sweep", "dnaldpc_get_trace", "dnaldpc_decode_window",
 ]
 
 
@@ -48,6 +48,11 @@ class Stats(C.Structure):
     _fields_ = [("frames", C.c_int64), ("frame_iters", C.c_int64), ("kernel_launches", C.c_int64),
                 ("waves", C.c_int64), ("row_ms", C.c_double), ("col_ms", C.c_double), ("total_ms", C.c_double),
                 ("compactions", C.c_int64)]
+
+
+class Window(C.Structure):
+    _fields_ = [("code_type", C.c_int32), ("L", C.c_int32), ("w", C.c_int32), ("win", C.c_int32),
+                ("Mv", C.c_void_p), ("Mc", C.c_void_p)]
 
 
 class LdpcError(RuntimeError):
@@ -95,6 +100,7 @@ def lib():
         L.dnaldpc_get_trace.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.dnaldpc_redecode_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.POINTER(Output), C.c_void_p]
+        L.dnaldpc_decode_window.argtypes = [C.c_void_p, C.POINTER(Window), C.c_void_p, C.c_int64, C.c_int, C.POINTER(Output)]
         _lib = L
     return _lib
 
@@ -212,6 +218,30 @@ class Decoder:
                                             C.byref(out), res["rounds"].ctypes.data))
         res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
                                     bitorder="little")[:, :N].astype(np.int8)
+        return res
+
+    def decode_window(self, lratio, max_iter, L, w, win, Mv, Mc, code_type=0, want=("bits", "iters", "ok")):
+        """Sliding-window BP for SC-LDPC codes (Run_SW_Decoder, dec.cpp:2092-2196). lratio: [F][N] p0/p1."""
+        N, M = self.code.N, self.code.M
+        lratio = np.ascontiguousarray(lratio, dtype=np.float64)
+        Mv = np.ascontiguousarray(Mv, dtype=np.int32); Mc = np.ascontiguousarray(Mc, dtype=np.int32)
+        F = lratio.shape[0]
+        wd = Window(code_type=code_type, L=L, w=w, win=win, Mv=Mv.ctypes.data, Mc=Mc.ctypes.data)
+        res, out = {}, Output()
+        if "bits" in want:
+            res["bits_packed"] = np.zeros((F, self.words_per_frame), np.uint32); out.bits = res["bits_packed"].ctypes.data
+        if "dblk" in want:
+            res["dblk"] = np.zeros((F, N), np.uint8); out.dblk = res["dblk"].ctypes.data
+        if "iters" in want:
+            res["iters"] = np.zeros(F, np.int32); out.iters = res["iters"].ctypes.data
+        if "ok" in want:
+            res["ok"] = np.zeros(F, np.uint8); out.is_codeword = res["ok"].ctypes.data
+        if "pchk" in want:
+            res["pchk"] = np.zeros((F, M), np.uint8); out.pchk = res["pchk"].ctypes.data
+        _check(lib().dnaldpc_decode_window(self._h, C.byref(wd), lratio.ctypes.data, F, max_iter, C.byref(out)))
+        if "bits" in want:
+            res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
+                                        bitorder="little")[:, :N].astype(np.int8)
         return res
 
     def run_bp_decoder(self, lratio, max_iter):

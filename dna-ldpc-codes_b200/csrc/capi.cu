@@ -215,6 +215,15 @@ int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int
     return DNALDPC_OK;
 }
 
+int dnaldpc_decode_window(dnaldpc_decoder *d, const dnaldpc_window *win, const double *lratio, int64_t F, int max_iter,
+                          const dnaldpc_output *out) {
+    if (!d || !win || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
+    const int rc = d->eng[0]->decode_window_host(d->c, *win, lratio, F, max_iter, *out);
+    if (rc) return set_err(rc, d->eng[0]->error());
+    d->stats = d->eng[0]->stats;
+    return DNALDPC_OK;
+}
+
 int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_iter, char *dblk, char *pchk,
                            int *is_codeword, int *iters) {
     if (!d || !lratio || !dblk) return set_err(DNALDPC_ERR_ARG, "null argument");

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "bp_kernels.cuh"
+#include "sw_kernels.cuh"
 
 namespace dnaldpc {
 
@@ -75,7 +76,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
-                    d_slot_, d_mv_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
+                    d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
@@ -488,6 +489,140 @@ int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const 
         CK(cudaStreamSynchronize(st));
     }
     stats = acc;
+    if (out.iters) for (int64_t f = 0; f < F; f++) stats.frame_iters += out.iters[f];
+    return DNALDPC_OK;
+}
+
+// ---- sliding-window BP for spatially-coupled codes ------------------------------------
+
+// Window ranges of every position, with the running sums of Run_SW_Decoder itself (dec.cpp:2115-2183).
+// Per position: {V_Start, V_End, C_Start, C_End, V_Check_End, C_Check_End, Init_from, Init_to}.
+static std::vector<int> sw_schedule(int M, int N, const dnaldpc_window &w) {
+    const int L = w.L, D = w.code_type == 0 ? L + w.w - 1 : L + (w.w - 1) / 2;
+    std::vector<int> s((size_t)8 * L);
+    int vs = 0, ve = 0, cs = 0, ce = 0, vce = 0, cce = 0;
+    for (int i = 0; i < w.w; i++) { vce += w.Mv[i]; cce += w.Mc[i]; }
+    for (int i = 0; i < w.win; i++) { ve += w.Mv[i]; ce += w.Mc[i]; }
+    for (int t = 0; t < L; t++) {
+        int init_from = ve, init_to = ve;
+        if (t == 0) init_from = 0;
+        else {
+            vs += w.Mv[t - 1];
+            cs += w.Mc[t - 1];
+            ve = (t + w.win >= L) ? N : ve + w.Mv[t + w.win - 1];
+            ce = (t + w.win >= D) ? M : ce + w.Mc[t + w.win - 1];
+            if (t + w.w >= L) { vce = N; cce = M; }
+            else { vce += w.Mv[t + w.w - 1]; cce += w.Mc[t + w.w - 1]; }
+            init_from = init_to = ve;
+            if (t + w.win <= L) init_from = ve - w.Mv[t + w.win - 1];
+        }
+        int *r = &s[(size_t)8 * t];
+        r[0] = vs; r[1] = ve; r[2] = cs; r[3] = ce; r[4] = vce; r[5] = cce; r[6] = init_from; r[7] = init_to;
+    }
+    return s;
+}
+
+int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const double *lratio, int64_t F, int max_iter,
+                               const dnaldpc_output &out) {
+    if (!err_.empty() && d_row_ptr_ == nullptr) return DNALDPC_ERR_CUDA;
+    err_.clear();
+    if (precision_ != DNALDPC_PREC_F64) return fail("the sliding-window decoder runs in fp64 only", DNALDPC_ERR_UNSUPPORTED);
+    if (F < 0 || max_iter < 0 || (F > 0 && !lratio) || out.posterior) return fail("bad argument", DNALDPC_ERR_ARG);
+    const int D = w.code_type == 0 ? w.L + w.w - 1 : w.L + (w.w - 1) / 2;
+    if (w.L < 1 || w.w < 1 || w.win < 1 || !w.Mv || !w.Mc || w.win > D || w.w > D) return fail("bad window description", DNALDPC_ERR_ARG);
+    const std::vector<int> sched = sw_schedule(M_, N_, w);
+    for (int t = 0; t < w.L; t++) {  // the ranges index H directly in the reference; reject what would run off the matrix there
+        const int *r = &sched[(size_t)8 * t];
+        if (r[0] < 0 || r[1] > N_ || r[0] > r[1] || r[2] < 0 || r[3] > M_ || r[2] > r[3] || r[4] > N_ || r[5] > M_ || r[6] < 0 || r[6] > r[7])
+            return fail("window ranges leave the parity-check matrix (Mv / Mc do not match the code)", DNALDPC_ERR_ARG);
+    }
+    if (F == 0) return DNALDPC_OK;
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = own_stream_;
+    stats = dnaldpc_stats{};
+    stats.frames = F;
+    const int G = (int)std::min<int64_t>((F + 31) / 32, wave_frames_ / 32);
+    int rc = ensure_slots(G, false);
+    if (rc) return rc;
+    if (G > sw_cap_groups_) {
+        if (d_sw_lr_) cudaFree(d_sw_lr_);
+        d_sw_lr_ = nullptr; sw_cap_groups_ = 0;
+        CK(cudaMalloc(&d_sw_lr_, std::max<size_t>((size_t)G * E_ * kFG * sizeof(double), 16)));
+        sw_cap_groups_ = G;
+    }
+    if (!d_edge_row_) {
+        std::vector<int32_t> er((size_t)std::max(E_, 1));
+        for (int i = 0; i < M_; i++)
+            for (int e = code.row_ptr[i]; e < code.row_ptr[i + 1]; e++) er[e] = i;
+        CK(cudaMalloc((void **)&d_edge_row_, er.size() * sizeof(int32_t)));
+        CK(cudaMemcpy(d_edge_row_, er.data(), er.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    SchedArrays s;
+    fill_sched(s);
+    uint32_t *runw = s.actw;
+    int32_t *n_pos = s.slot_iter, *sum = s.harv_iter;
+    unsigned *remaining = d_counters_;
+    double *pr = (double *)d_msg_, *lr = (double *)d_sw_lr_, *lrat = (double *)d_lratio_;
+    const size_t wpf = (size_t)(N_ + 31) / 32;
+    const int64_t S = (int64_t)G * kFG;
+    for (int64_t f0 = 0; f0 < F; f0 += S) {
+        const int nf = (int)std::min<int64_t>(S, F - f0);
+        const int Gw = (nf + 31) / 32;
+        if (!stage(&s_in_, &c_in_, (size_t)nf * N_ * 8)) return fail("out of device memory (input staging)", DNALDPC_ERR_NOMEM);
+        CK(cudaMemcpyAsync(s_in_, lratio + (size_t)f0 * N_, (size_t)nf * N_ * 8, cudaMemcpyHostToDevice, st));
+        dnaldpc_output o{};
+        if (out.bits && !(o.bits = (uint32_t *)stage(&s_bits_, &c_bits_, (size_t)nf * wpf * 4))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        if (out.dblk && !(o.dblk = (uint8_t *)stage(&s_dblk_, &c_dblk_, (size_t)nf * N_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        if (out.pchk && !(o.pchk = (uint8_t *)stage(&s_pchk_, &c_pchk_, (size_t)nf * M_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        rc = ensure_frame_scratch(nf);
+        if (rc) return rc;
+        sw_load_kernel<<<dim3((unsigned)((N_ + 31) / 32), (unsigned)Gw), 256, 0, st>>>((const double *)s_in_, lrat, d_decw_, N_, nf);
+        CK(cudaMemsetAsync(pr, 0, (size_t)Gw * E_ * kFG * sizeof(double), st));  // alloc_entry: e->pr = e->lr = 0
+        CK(cudaMemsetAsync(lr, 0, (size_t)Gw * E_ * kFG * sizeof(double), st));
+        stats.kernel_launches++;
+        for (int t = 0; t < w.L; t++) {
+            const int *r = &sched[(size_t)8 * t];
+            sw_begin_kernel<<<(Gw * kFG + 255) / 256, 256, 0, st>>>(runw, n_pos, sum, Gw, nf, t == 0);
+            stats.kernel_launches++;
+            if (r[7] > r[6]) {
+                sw_init_kernel<<<dim3((unsigned)((r[7] - r[6] + 7) / 8), (unsigned)Gw), 256, 0, st>>>(pr, lr, lrat, d_col_ptr_, d_col_edge_, N_, E_, r[6], r[7]);
+                stats.kernel_launches++;
+            }
+            for (int it = 0; it <= max_iter; it++) {  // every position runs at least one update, at most max_iter + 1
+                if (r[3] > r[2]) {
+                    const long long items = (long long)Gw * (r[3] - r[2]);
+                    sw_row_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(pr, lr, runw, d_row_ptr_, E_, r[2], r[3], Gw);
+                    stats.kernel_launches++;
+                }
+                if (r[1] > r[0]) {
+                    sw_col_kernel<<<dim3((unsigned)((r[1] - r[0] + 7) / 8), (unsigned)Gw), 256, 0, st>>>(
+                        pr, lr, lrat, d_decw_, runw, d_col_ptr_, d_col_edge_, d_edge_row_, N_, E_, r[0], r[1], r[2], r[3]);
+                    stats.kernel_launches++;
+                }
+                CK(cudaMemsetAsync(remaining, 0, sizeof(unsigned), st));
+                sw_syn_kernel<<<Gw, 256, 0, st>>>(d_decw_, runw, n_pos, sum, d_row_ptr_, d_col_idx_, N_, M_, r[0], r[4], r[2], r[5],
+                                                  max_iter, remaining, 0, w.L, nf, 0, nullptr, nullptr, nullptr);
+                stats.kernel_launches++;
+                CK(cudaMemcpyAsync(h_counters_, remaining, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (h_counters_[0] == 0) break;
+            }
+        }
+        sw_syn_kernel<<<Gw, 256, 0, st>>>(d_decw_, runw, n_pos, sum, d_row_ptr_, d_col_idx_, N_, M_, 0, N_, 0, M_, max_iter, remaining, 1,
+                                          w.L, nf, 0, d_iters_, d_ok_, o.pchk);
+        stats.kernel_launches++;
+        if (o.bits || o.dblk) {
+            sw_output_kernel<<<dim3((unsigned)((wpf + 255) / 256), (unsigned)nf), 256, 0, st>>>(d_decw_, N_, nf, 0, (int)wpf, o.bits, o.dblk);
+            stats.kernel_launches++;
+        }
+        CK(cudaGetLastError());
+        if (out.bits) CK(cudaMemcpyAsync(out.bits + (size_t)f0 * wpf, o.bits, (size_t)nf * wpf * 4, cudaMemcpyDeviceToHost, st));
+        if (out.dblk) CK(cudaMemcpyAsync(out.dblk + (size_t)f0 * N_, o.dblk, (size_t)nf * N_, cudaMemcpyDeviceToHost, st));
+        if (out.pchk) CK(cudaMemcpyAsync(out.pchk + (size_t)f0 * M_, o.pchk, (size_t)nf * M_, cudaMemcpyDeviceToHost, st));
+        if (out.iters) CK(cudaMemcpyAsync(out.iters + f0, d_iters_, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        if (out.is_codeword) CK(cudaMemcpyAsync(out.is_codeword + f0, d_ok_, (size_t)nf, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     if (out.iters) for (int64_t f = 0; f < F; f++) stats.frame_iters += out.iters[f];
     return DNALDPC_OK;
 }

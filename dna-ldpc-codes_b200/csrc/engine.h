@@ -27,6 +27,9 @@ class Engine {
     int decode_device(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out, cudaStream_t stream);
     // HOST pointers; blocking.
     int decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out);
+    // Sliding-window BP for spatially-coupled codes (Run_SW_Decoder, dec.cpp:2092-2196); HOST pointers; blocking.
+    int decode_window_host(const Code &code, const dnaldpc_window &w, const double *lratio, int64_t F, int max_iter,
+                           const dnaldpc_output &out);
     int synth_bsc(const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0, int64_t F, double eps,
                   uint32_t *out_bits, cudaStream_t stream);
 
@@ -65,6 +68,9 @@ class Engine {
     uint32_t *d_decw_ = nullptr, *d_masks_ = nullptr;  // masks: 6 words per group (act, done, newf, fresh, harv, unsat)
     unsigned int *d_arrive_ = nullptr;
     int32_t *d_slot_ = nullptr;                          // 4 ints per slot (frame, iter, harv_frame, harv_iter)
+    void *d_sw_lr_ = nullptr;                            // sliding-window mode: second message array (check -> bit)
+    int sw_cap_groups_ = 0;
+    int32_t *d_edge_row_ = nullptr;                      // sliding-window mode: check of every edge
     int32_t *d_mv_ = nullptr;                            // drain-tail compaction: src[S], dst[S], {count, K}
     static constexpr int kCompactNum = 1, kCompactDen = 2;  // compact when busy slots <= 1/2 of the packed region
     unsigned long long *d_next_ = nullptr;

@@ -1,0 +1,223 @@
+// sw_kernels.cuh - sliding-window belief propagation for spatially-coupled LDPC codes.
+//
+// Reference: Run_SW_Decoder (dec.cpp:2092-2196) with Init_SW_Decoder (2366-2386), Iter_SW_Decoder (2388-2432),
+// Check_Update_SW (2478-2500), Variable_Update_SW (2502-2548), Decision_SW (2630-2645), check_bound (check.cpp:49-72)
+// -> mod2sparse_mulvec_bound (mod2sparse.cpp:883-912).
+//
+// Same slot-interleaved layout as the flooding decoder (bp_kernels.cuh): a warp is one node x the 32 frames of a group.
+// Differences that follow from the algorithm:
+//   * a bit that has left the window keeps its bit->check message while the checks it still touches keep running, so
+//     e->pr and e->lr are both live: TWO message arrays pr[G][E][32], lr[G][E][32], both zero at the start
+//     (alloc_entry, mod2sparse.cpp:61-62);
+//   * the frames of a wave walk through the window positions together: a frame that satisfies the bounded syndrome of
+//     position t early waits (its messages untouched) until the slowest frame of the wave has finished t. Frames are
+//     independent, so each frame's arithmetic - and hence its result - is exactly the reference's;
+//   * the arithmetic uses nvcc's full-range IEEE division (the check_*_slow helpers): this mode is about coverage,
+//     the hand-tuned in-range sequences stay with the hot flooding kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bp_kernels.cuh"
+
+namespace dnaldpc {
+
+// Frame-major host layout -> slot-interleaved lratio; every decision starts "set": the reference hands Run_SW_Decoder
+// a dblk buffer filled with 2 (DNA_main.cpp:664-666) and mulvec_bound tests u[j] != 0.
+__global__ void __launch_bounds__(256)
+sw_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint32_t *__restrict__ decw, int N, int nf) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, g = blockIdx.y, j0 = blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit
+        const int slot = g * kFG + r, j = j0 + tx;
+        tile[r][tx] = (slot < nf && j < N) ? in[(size_t)slot * N + j] : 1.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {  // r = bit, tx = slot
+        const int j = j0 + r;
+        if (j < N) {
+            lratio[((size_t)g * N + j) * kFG + tx] = tile[tx][r];
+            if (tx == 0) decw[(size_t)g * N + j] = 0xffffffffu;
+        }
+    }
+}
+
+// Start of a window position: every frame of the wave runs again, per-position iteration count n = 0.
+__global__ void sw_begin_kernel(uint32_t *__restrict__ runw, int32_t *__restrict__ n_pos, int32_t *__restrict__ sum, int G, int nf,
+                                int first) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= G * kFG) return;
+    n_pos[slot] = 0;
+    if (first) sum[slot] = 0;
+    if ((slot & 31) == 0) {
+        const int left = nf - slot;
+        runw[slot >> 5] = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+    }
+}
+
+// Init_SW_Decoder: e->pr = lratio[j], e->lr = 1 for every entry of the columns [j0, j1).
+__global__ void __launch_bounds__(256)
+sw_init_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *__restrict__ lratio,
+               const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N, int E, int j0, int j1) {
+    const int lane = threadIdx.x & 31, g = blockIdx.y;
+    const int j = j0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= j1) return;
+    const double v = lratio[((size_t)g * N + j) * kFG + lane];
+    for (int k = __ldg(col_ptr + j); k < __ldg(col_ptr + j + 1); k++) {
+        const size_t idx = ((size_t)g * E + __ldg(col_edge + k)) * kFG + lane;
+        pr[idx] = v;
+        lr[idx] = 1.0;
+    }
+}
+
+// Check_Update_SW for the checks [c0, c1): the whole row, whatever window its bits are in. The forward products are
+// parked in e->lr exactly like the reference does.
+__global__ void __launch_bounds__(128)
+sw_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, const uint32_t *__restrict__ runw,
+              const int32_t *__restrict__ row_ptr, int E, int c0, int c1, int G) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int rows = c1 - c0;
+    if (item >= (long long)G * rows) return;
+    const int g = (int)(item / rows), i = c0 + (int)(item - (long long)g * rows);
+    if (!((runw[g] >> lane) & 1u)) return;
+    const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
+    const double *p = pr + (size_t)g * E * kFG + lane;
+    double *l = lr + (size_t)g * E * kFG + lane;
+    double dl = 1.0;
+    for (int e = e0; e < e1; e++) {
+        l[(size_t)e * kFG] = dl;
+        dl = __dmul_rn(dl, check_factor_slow(p[(size_t)e * kFG]));
+    }
+    dl = 1.0;
+    for (int e = e1 - 1; e >= e0; e--) {
+        const double t = __dmul_rn(l[(size_t)e * kFG], dl);
+        l[(size_t)e * kFG] = check_to_bit_slow(t);
+        dl = __dmul_rn(dl, check_factor_slow(p[(size_t)e * kFG]));
+    }
+}
+
+// Variable_Update_SW + Decision_SW for the bits [v0, v1), restricted to the entries whose check lies in [c0, c1).
+// The decision's product lratio * lr * ... (Decision_SW) is the forward product of the update (same factors, same
+// order); no NaN guard on it: NaN <= 1 is false -> bit 0, like the reference.
+__global__ void __launch_bounds__(256)
+sw_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
+              uint32_t *__restrict__ decw, const uint32_t *__restrict__ runw, const int32_t *__restrict__ col_ptr,
+              const int32_t *__restrict__ col_edge, const int32_t *__restrict__ edge_row, int N, int E, int v0, int v1, int c0,
+              int c1) {
+    const int lane = threadIdx.x & 31, g = blockIdx.y;
+    const int j = v0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= v1) return;
+    const uint32_t run = runw[g];
+    if (run == 0) return;
+    const bool on = (run >> lane) & 1u;
+    const int k0 = __ldg(col_ptr + j), k1 = __ldg(col_ptr + j + 1);
+    double *p = pr + (size_t)g * E * kFG + lane;
+    const double *l = lr + (size_t)g * E * kFG + lane;
+    double acc = on ? lratio[((size_t)g * N + j) * kFG + lane] : 1.0;
+    if (on) {
+        for (int k = k0; k < k1; k++) {
+            const int e = __ldg(col_edge + k), r = __ldg(edge_row + e);
+            if (r < c1 && r >= c0) {
+                p[(size_t)e * kFG] = acc;
+                acc = __dmul_rn(acc, l[(size_t)e * kFG]);
+            }
+        }
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, acc <= 1.0);
+    if (lane == 0) {
+        uint32_t *dst = decw + (size_t)g * N + j;
+        *dst = (w & run) | (*dst & ~run);
+    }
+    if (on) {
+        double s = 1.0;
+        for (int k = k1 - 1; k >= k0; k--) {
+            const int e = __ldg(col_edge + k), r = __ldg(edge_row + e);
+            if (r < c1 && r >= c0) {
+                double v = __dmul_rn(p[(size_t)e * kFG], s);
+                if (v != v) v = 1.0;
+                p[(size_t)e * kFG] = v;
+                s = __dmul_rn(s, l[(size_t)e * kFG]);
+            }
+        }
+    }
+}
+
+// check_bound + the loop control of Iter_SW_Decoder (dec.cpp:2418-2428), one CTA per group: parity of the checks
+// [c0, cc) over the bits [v0, vc) for the 32 frames at once. A running frame whose bounded syndrome is zero, or whose
+// count n has reached max_iter, is finished with this position (n is added to its sum); the others iterate once more.
+// `final`: the closing check() of Run_SW_Decoder (dec.cpp:2187-2189) over the whole matrix -> success flag, iteration
+// figure floor(sum / L) (dec.cpp:2193-2194) and, on request, the syndrome bytes.
+__global__ void __launch_bounds__(256)
+sw_syn_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ runw, int32_t *__restrict__ n_pos,
+              int32_t *__restrict__ sum, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int N, int M,
+              int v0, int vc, int c0, int cc, int max_iter, unsigned int *__restrict__ remaining, int final, int L, int nf,
+              long long frame0, int32_t *__restrict__ iters_out, uint8_t *__restrict__ ok_out, uint8_t *__restrict__ pchk_out) {
+    const int g = blockIdx.x;
+    const uint32_t run = runw[g];
+    const int left = nf - g * kFG;
+    const uint32_t valid = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+    if (!final && run == 0) return;
+    const uint32_t *dw = decw + (size_t)g * N;
+    uint32_t acc = 0;
+    for (int i = c0 + threadIdx.x; i < cc; i += blockDim.x) {
+        uint32_t p = 0;
+        for (int e = __ldg(row_ptr + i); e < __ldg(row_ptr + i + 1); e++) {
+            const int c = __ldg(col_idx + e);
+            if (c >= v0 && c < vc) p ^= dw[c];
+        }
+        acc |= p;
+        if (final && pchk_out)
+            for (uint32_t m = valid; m; m &= m - 1) {
+                const int f = __ffs(m) - 1;
+                pchk_out[(size_t)(frame0 + g * kFG + f) * M + i] = (uint8_t)((p >> f) & 1u);
+            }
+    }
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    __shared__ uint32_t s_or[8];
+    if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    uint32_t unsat = 0;
+    for (int w = 0; w < 8; w++) unsat |= s_or[w];
+    const int f = threadIdx.x, slot = g * kFG + f;
+    if (final) {
+        if ((valid >> f) & 1u) {
+            ok_out[frame0 + slot] = (uint8_t)(((unsat >> f) & 1u) ^ 1u);
+            iters_out[frame0 + slot] = sum[slot] / L;
+        }
+        return;
+    }
+    const bool running = (run >> f) & 1u;
+    bool cont = false;
+    if (running) {
+        const int n = n_pos[slot];
+        if (n == max_iter || !((unsat >> f) & 1u)) sum[slot] += n;
+        else { n_pos[slot] = n + 1; cont = true; }
+    }
+    const uint32_t next = __ballot_sync(0xffffffffu, cont);
+    if (f == 0) {
+        runw[g] = next;
+        if (next) atomicAdd(remaining, (unsigned)__popc(next));
+    }
+}
+
+// Decisions of a wave back to frame-major outputs (packed words and / or 0-1 chars).
+__global__ void __launch_bounds__(256)
+sw_output_kernel(const uint32_t *__restrict__ decw, int N, int nf, long long frame0, int wpf, uint32_t *__restrict__ bits,
+                 uint8_t *__restrict__ dblk) {
+    const int slot = blockIdx.y, w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nf || w >= wpf) return;
+    const uint32_t *dw = decw + (size_t)(slot >> 5) * N;
+    const int f = slot & 31;
+    uint32_t word = 0;
+    for (int b = 0; b < 32; b++) {
+        const int j = w * 32 + b;
+        const uint32_t bit = j < N ? ((dw[j] >> f) & 1u) : 0u;
+        word |= bit << b;
+        if (dblk && j < N) dblk[(size_t)(frame0 + slot) * N + j] = (uint8_t)bit;
+    }
+    if (bits) bits[(size_t)(frame0 + slot) * wpf + w] = word;
+}
+
+}  // namespace dnaldpc

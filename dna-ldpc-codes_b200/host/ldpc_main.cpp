@@ -6,7 +6,10 @@
 // Reads <codeword_base>.txt (true codeword), <soft_base>.txt (LLR = ln(p0/p1)) and <pchk_base>.pchk from the CWD,
 // writes dec_<codeword_base>.txt, result_(...).txt and the same stdout summary as the reference
 // (Set_Code :552-556, Run_Simulation :916-927, Print_One_Result :1170-1182, Print_All_Result :1048-1123).
-// Decoder types 0 (BP) and 20-22 (floating min-sum) without punctuation / shortening / targeting; anything else is rejected.
+// Decoder types 0 (BP), 20-22 (floating min-sum) and 60 (sliding-window BP for spatially-coupled codes) without
+// punctuation / shortening / targeting; anything else is rejected. Type 60 takes the reference's extra block
+// `<code_type> <w> <L> <WIN>` after <targeting> and reads the per-position node counts (SC_D lines of Mv, then SC_D lines
+// of Mc) from <pchk_base>.txt (DNA_main.cpp:424-464). Its POSITION_BER_*.txt diagnostic is not written.
 //
 // Extensions (after the positional block, none of them changes the reference behaviour when absent):
 //   --device N        CUDA device ordinal (default 0)
@@ -38,6 +41,7 @@ struct Args {
     std::string cw_base, soft_base, pchk_base;
     double chan_param = 0;
     int punctuation = 0, shortening = 0, targeting = 0;
+    int sc_code_type = 0, sc_w = 0, sc_L = 0, sc_win = 0;  // decoder type 60 only
     int device = 0;
     bool fp32 = false, timing = false;
     std::string list;
@@ -75,6 +79,12 @@ Args parse(int argc, char **argv) {
     a.punctuation = atoi(next());
     a.shortening = atoi(next());
     a.targeting = atoi(next());
+    if (a.decoder_type == 60 && !a.punctuation && !a.shortening && !a.targeting) {  // DNA_main.cpp:424-429
+        a.sc_code_type = atoi(next());
+        a.sc_w = atoi(next());
+        a.sc_L = atoi(next());
+        a.sc_win = atoi(next());
+    }
     if (p != pos.size()) die_argc();
     return a;
 }
@@ -93,8 +103,9 @@ int main(int argc, char **argv) {
     // 0 = belief propagation; 20/21/22 = min-sum: with g_precision == 0 (the CLI cannot set it) all three reach the
     // floating-point Run_MSA_Decoder_INF (DNA_main.cpp:1588-1594)
     const bool minsum = a.decoder_type == 20 || a.decoder_type == 21 || a.decoder_type == 22;
-    if (a.decoder_type != 0 && !minsum) {
-        fprintf(stderr, "ldpc: decoder type %d is not supported by this build (0 = belief propagation, 20-22 = floating min-sum)\n", a.decoder_type);
+    const bool window = a.decoder_type == 60;
+    if (a.decoder_type != 0 && !minsum && !window) {
+        fprintf(stderr, "ldpc: decoder type %d is not supported by this build (0 = belief propagation, 20-22 = floating min-sum, 60 = sliding window)\n", a.decoder_type);
         return 1;
     }
     if (a.punctuation || a.shortening || a.targeting) {
@@ -120,6 +131,23 @@ int main(int argc, char **argv) {
     const double std_dev = dnaldpc_std_dev(ebno, rate);
     int dv, rdv, dc, rdc;
     dnaldpc_code_check_regular(code, &dv, &rdv, &dc, &rdc);  // LDPC_Set_Decoder -> CheckRegular
+
+    // sliding window: per-position node counts from <pchk_base>.txt (SC_D values of Mv, then SC_D of Mc; DNA_main.cpp:431-462)
+    std::vector<int32_t> sc_mv, sc_mc;
+    if (window) {
+        if (a.sc_L < 1 || a.sc_w < 1 || a.sc_win < 1) { fprintf(stderr, "ldpc: bad sliding-window parameters (w, L, WIN must be >= 1)\n"); return 1; }
+        const int D = a.sc_code_type == 0 ? a.sc_L + a.sc_w - 1 : a.sc_L + (a.sc_w - 1) / 2;
+        const std::string mfile = a.pchk_base + ".txt";
+        FILE *f = fopen(mfile.c_str(), "r");
+        if (!f) { fprintf(stderr, "Can't open node-count file: %s\n", mfile.c_str()); return 1; }
+        sc_mv.assign((size_t)D, 0);
+        sc_mc.assign((size_t)D, 0);
+        bool ok = true;
+        for (int i = 0; i < D && ok; i++) ok = fscanf(f, "%d", &sc_mv[(size_t)i]) == 1;
+        for (int i = 0; i < D && ok; i++) ok = fscanf(f, "%d", &sc_mc[(size_t)i]) == 1;
+        fclose(f);
+        if (!ok) { fprintf(stderr, "Node-count file %s holds fewer than 2 x %d integers\n", mfile.c_str(), D); return 1; }
+    }
 
     // frames: the positional pair, or every pair of --list
     std::vector<std::pair<std::string, std::string>> frames;
@@ -181,7 +209,13 @@ int main(int argc, char **argv) {
     out.iters = iters.data();
     out.is_codeword = okflag.data();
     auto c0 = std::chrono::steady_clock::now();
-    check(dnaldpc_decode_batch(dec, &in, (int64_t)F, a.max_iter, &out));  // LDPC_Decode -> Run_Belief_Propagation_Decoder
+    if (window) {  // LDPC_Decode -> Run_SW_Decoder (DNA_main.cpp:1599-1602)
+        dnaldpc_window wd{};
+        wd.code_type = a.sc_code_type; wd.L = a.sc_L; wd.w = a.sc_w; wd.win = a.sc_win;
+        wd.Mv = sc_mv.data(); wd.Mc = sc_mc.data();
+        check(dnaldpc_decode_window(dec, &wd, lr.data(), (int64_t)F, a.max_iter, &out));
+    } else
+        check(dnaldpc_decode_batch(dec, &in, (int64_t)F, a.max_iter, &out));  // LDPC_Decode -> Run_Belief_Propagation_Decoder
     auto c1 = std::chrono::steady_clock::now();
 
     // error counting: LDPC_Raw_Error_Check (:1711-1750, sign of the LLR) and LDPC_BIT_Check (:1675-1706)
@@ -247,6 +281,7 @@ int main(int argc, char **argv) {
     fprintf(fp, "bRegular_dv   : %d\n", rdv);
     fprintf(fp, "dc            : %d\n", dc);
     fprintf(fp, "bRegular_dc   : %d\n", rdc);
+    if (window) fprintf(fp, "w   : %d\n\nL   : %d\n\nW   : %d\n\n", a.sc_w, a.sc_L, a.sc_win);  // DNA_main.cpp:1069-1071
     fprintf(fp, "=============================================\n");
     fprintf(fp, "                 result\n");
     fprintf(fp, "=============================================\n");

@@ -140,6 +140,24 @@ int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_ite
 int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
                            int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds);
 
+/* Sliding-window belief propagation for spatially-coupled (SC-LDPC) codes = Run_SW_Decoder (dec.cpp:2092-2196; decoder
+ * type 60 of the reference CLI, DNA_main.cpp:1599-1602) with Init_SW_Decoder / Iter_SW_Decoder / Check_Update_SW /
+ * Variable_Update_SW / Decision_SW (dec.cpp:2366-2645) and check_bound (check.cpp:49-72). The window description is the
+ * reference's argument list: code_type (0: two-sided termination, SC_D = L + w - 1 positions of checks; otherwise
+ * L + (w-1)/2), coupling length L, coupling width w, window size win (all in positions) and the per-position node
+ * counts Mv[SC_D], Mc[SC_D] (g_SC_CODE_M / g_SC_CODE_Mc, DNA_main.cpp:440-462). Columns / rows of H are ordered by
+ * position. lratio: HOST double [F][N], p0/p1. Outputs (HOST; posterior must be NULL): bits / dblk = final decisions,
+ * iters = floor(sum over positions of Iter_SW_Decoder's n / L) as returned by the reference, is_codeword and pchk from
+ * the closing check(). Bits no window has decided yet count as set in the bounded syndromes, as with the reference's
+ * dblk buffer pre-filled with 2 (DNA_main.cpp:664-666). The position_BER diagnostic (test_BER) is not produced.
+ * fp64 only; runs on the decoder's first device. */
+typedef struct dnaldpc_window {
+    int32_t code_type, L, w, win;
+    const int32_t *Mv, *Mc;
+} dnaldpc_window;
+int dnaldpc_decode_window(dnaldpc_decoder *d, const dnaldpc_window *win, const double *lratio, int64_t F, int max_iter,
+                          const dnaldpc_output *out);
+
 /* ---- likelihood-setup helpers (host) ----------------------------------------------------------- */
 double dnaldpc_std_dev(double ebno_db, double rate);                  /* getStd_dev, channel.cpp:9-16 */
 int dnaldpc_vote_table(double eps, double *table256);                 /* table[k+128] = exp(k*ln((1-eps)/eps)) */

@@ -103,3 +103,34 @@ def test_cli_side_by_side_with_reference_binary(tmp_path, dectype):
         outs[who] = (r.stdout, open(os.path.join(d, "dec_%s.txt" % cwname), "rb").read(), res[0],
                      _strip_times(open(os.path.join(d, res[0])).read()))
     assert outs["ours"] == outs["ref"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ldpc_ref not built")
+def test_cli_sliding_window_side_by_side(tmp_path):
+    """Decoder type 60 (sliding-window BP, Run_SW_Decoder) with the reference's own argument block
+    `<code_type> <w> <L> <WIN>` and node-count file <pchk_base>.txt: stdout, dec file, result-file name and the result
+    file up to its BER lines (which the reference computes from an uninitialised counter) must equal the
+    unmodified reference CLI's. The POSITION_BER diagnostic file is not produced."""
+    g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
+    N, D = 768, 14
+    rs = np.random.RandomState(8)
+    llr = np.where(rs.rand(N) < 0.05, -1.0, 1.0) * rs.uniform(1.0, 4.0, N)
+    outs = {}
+    for who, exe in (("ours", LDPC), ("ref", REF_CLI)):
+        d = str(tmp_path / who)
+        os.makedirs(d)
+        shutil.copyfile(os.path.join(ol.GOLDEN, "sc_z32_l12.pchk"), os.path.join(d, "sc.pchk"))
+        with open(os.path.join(d, "sc.txt"), "w") as fh:
+            fh.write("".join("%d\n" % v for v in g["Mv"]) + "".join("%d\n" % v for v in g["Mc"]))
+        with open(os.path.join(d, "cw.txt"), "w") as fh:
+            fh.write("0 " * N)
+        with open(os.path.join(d, "soft.txt"), "w") as fh:
+            fh.write(" ".join(repr(float(x)) for x in llr))
+        r = subprocess.run([exe, "0", "60", "0", "7", "20", "1", "cw", "soft", "sc", "0", "0", "0", "0", "0", "3", "12", "4"], cwd=d, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        res = [f for f in os.listdir(d) if f.startswith("result_")]
+        assert len(res) == 1
+        body = _strip_times(open(os.path.join(d, res[0])).read())
+        outs[who] = (r.stdout, open(os.path.join(d, "dec_cw.txt"), "rb").read(), res[0], [l for l in body if not l.startswith("BER[")])
+    assert outs["ours"] == outs["ref"]
+    assert len(g["Mv"]) == D

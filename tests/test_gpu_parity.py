@@ -411,6 +411,46 @@ def test_drain_tail_compaction(code18432, orc18432, cws):
         assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
 
 
+def test_sliding_window_decoder():
+    """sliding-window BP for SC-LDPC codes (dnaldpc_decode_window = Run_SW_Decoder, dec.cpp:2092-2196) on the
+    generated (3,6) SC code: (a) the golden vectors produced by the unmodified reference, (b) a ragged batch (frames that
+    leave a window position after 0..max_iter extra updates share warp groups; two waves) against the oracle, for
+    several window sizes incl. win == L (one window over the whole code)."""
+    g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
+    path = os.path.join(ol.GOLDEN, "sc_z32_l12.pchk")
+    code = ldpc.Code(path)
+    orc = ol.Oracle(path)
+    Mv, Mc, L, w = g["Mv"], g["Mc"], int(g["L"]), int(g["w"])
+    N = code.N
+    dec = ldpc.Decoder(code, wave_frames=64)
+    want = ("bits", "dblk", "iters", "ok", "pchk")
+    for name in g["names"]:
+        name = str(name)
+        r = dec.decode_window(g[name + ".lratio"][None, :], int(g[name + ".max_iter"]), L, w, int(g[name + ".win"]), Mv, Mc, want=want)
+        assert r["iters"][0] == int(g[name + ".n"]) and r["ok"][0] == int(g[name + ".ok"]), name
+        assert np.array_equal(np.packbits(r["bits"][0].astype(np.uint8), bitorder="little"), g[name + ".dblk"]), name
+        assert np.array_equal(r["dblk"][0], r["bits"][0]), name
+        assert np.array_equal(np.packbits(r["pchk"][0], bitorder="little"), g[name + ".pchk"]), name
+    rs = np.random.RandomState(4242)
+    F = 100
+    eps = rs.choice([0.0, 0.03, 0.05, 0.065, 0.08, 0.11], size=F)
+    llr = np.where(rs.rand(F, N) < eps[:, None], -1.0, 1.0) * rs.uniform(1.0, 4.0, (F, N))
+    llr[rs.rand(F, N) < 0.02] = 0.0
+    lr = np.exp(llr)
+    seen = set()
+    for win, mi in [(3, 12), (4, 25), (12, 8), (5, 0)]:
+        r = dec.decode_window(lr, mi, L, w, win, Mv, Mc, want=want)
+        for f in range(F):
+            o = orc.decode_sw(lr[f], mi, L, w, win, Mv, Mc)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (win, mi, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (win, mi, f)
+            seen.add(o["n"])
+    assert len(seen) > 5
+    with pytest.raises(ldpc.LdpcError):  # node counts that do not match the matrix
+        dec.decode_window(lr[:2], 5, L, w, 4, Mv * 2, Mc)
+    dec.close()
+
+
 def test_smem_check_kernel_mixed_groups_in_subprocess():
     """The shared-memory check kernel normally runs only in the steady state (full groups, nobody admitted). Its
     cp.async path for mixed groups (fresh / idle lanes) is forced here with the A/B switch, in a child process
