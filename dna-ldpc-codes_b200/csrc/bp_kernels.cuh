@@ -294,20 +294,37 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
 // ------------------------------------------------------------------------------------------------
 constexpr int kColWarps = 8;
 
-template <typename T, int DV, bool EXACT, int ALG>
-__device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restrict__ lratio, T *__restrict__ post,
-                                           const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
-                                           int N, int E, int g, int j, int f, bool on) {
-    const int c0 = EXACT ? j * DV : __ldg(col_ptr + j);
-    const int deg = EXACT ? DV : (__ldg(col_ptr + j + 1) - c0);
-    T *gmsg = msg + (size_t)g * E * kFG + f;
+// Loads of one (bit, slot): edge ids, the check->bit messages and the channel ratio. Kept apart from the arithmetic so
+// that the fp32 kernel can have the loads of two bits in flight before the first one's stores (which the compiler must
+// otherwise keep ahead of the next bit's loads: same array).
+template <typename T, int DV>
+struct ColIn {
     int eid[DV];
-#pragma unroll
-    for (int k = 0; k < DV; k++) eid[k] = (EXACT || k < deg) ? __ldg(col_edge + c0 + k) : 0;
     T lr[DV];
+    T P;
+    int deg;
+};
+
+template <typename T, int DV, bool EXACT>
+__device__ __forceinline__ void col_load(ColIn<T, DV> &c, const T *__restrict__ gmsg, const T *__restrict__ lratio,
+                                         const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N,
+                                         int g, int j, int f, bool on) {
+    const int c0 = EXACT ? j * DV : __ldg(col_ptr + j);
+    c.deg = EXACT ? DV : (__ldg(col_ptr + j + 1) - c0);
 #pragma unroll
-    for (int k = 0; k < DV; k++) lr[k] = (on && (EXACT || k < deg)) ? ld_stream(gmsg + (size_t)eid[k] * kFG) : T(1);
-    T P = on ? __ldg(lratio + ((size_t)g * N + j) * kFG + f) : T(1);
+    for (int k = 0; k < DV; k++) c.eid[k] = (EXACT || k < c.deg) ? __ldg(col_edge + c0 + k) : 0;
+#pragma unroll
+    for (int k = 0; k < DV; k++) c.lr[k] = (on && (EXACT || k < c.deg)) ? ld_stream(gmsg + (size_t)c.eid[k] * kFG) : T(1);
+    c.P = on ? __ldg(lratio + ((size_t)g * N + j) * kFG + f) : T(1);
+}
+
+template <typename T, int DV, bool EXACT, int ALG>
+__device__ __forceinline__ bool col_finish(const ColIn<T, DV> &c, T *__restrict__ gmsg, T *__restrict__ post, int N, int g, int j,
+                                           int f, bool on) {
+    const int deg = c.deg;
+    const int (&eid)[DV] = c.eid;
+    const T (&lr)[DV] = c.lr;
+    T P = c.P;
     if (ALG == ALG_MINSUM) {  // lr[] = c2v LLRs, P = channel LLR; sums in ascending row order, own edge skipped
         const T llr = P;
 #pragma unroll
@@ -349,7 +366,7 @@ __device__ __forceinline__ bool col_thread(T *__restrict__ msg, const T *__restr
 }
 
 template <typename T, int DV, bool EXACT, int ALG>
-__global__ void __launch_bounds__(kColWarps * 32)
+__global__ void __launch_bounds__(kColWarps * 32, DV <= 8 ? 4 : 1)
 col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__restrict__ decw,
                 const uint32_t *__restrict__ actw, T *__restrict__ post, const int32_t *__restrict__ col_ptr,
                 const int32_t *__restrict__ col_edge, int N, int E, int g0, int cols_per_warp) {
@@ -360,13 +377,28 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
     const bool on = (act >> lane) & 1u;
     const int jbeg = (blockIdx.x * kColWarps + warp) * cols_per_warp;
     const int jend = min(jbeg + cols_per_warp, N);
-    for (int j = jbeg; j < jend; j++) {
-        const bool bit = col_thread<T, DV, EXACT, ALG>(msg, lratio, post, col_ptr, col_edge, N, E, g, j, lane, on);
+    T *gmsg = msg + (size_t)g * E * kFG + lane;
+    auto put = [&](int j, bool bit) {
         const uint32_t w = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) {
             uint32_t *dst = decw + (size_t)g * N + j;
             *dst = (act == 0xffffffffu) ? w : ((w & act) | (*dst & ~act));
         }
+    };
+    int j = jbeg;
+    if (sizeof(T) == 4) {  // fp32: 128-byte requests -> two bits' loads in flight per thread
+        for (; j + 1 < jend; j += 2) {
+            ColIn<T, DV> a, b;
+            col_load<T, DV, EXACT>(a, gmsg, lratio, col_ptr, col_edge, N, g, j, lane, on);
+            col_load<T, DV, EXACT>(b, gmsg, lratio, col_ptr, col_edge, N, g, j + 1, lane, on);
+            put(j, col_finish<T, DV, EXACT, ALG>(a, gmsg, post, N, g, j, lane, on));
+            put(j + 1, col_finish<T, DV, EXACT, ALG>(b, gmsg, post, N, g, j + 1, lane, on));
+        }
+    }
+    for (; j < jend; j++) {
+        ColIn<T, DV> a;
+        col_load<T, DV, EXACT>(a, gmsg, lratio, col_ptr, col_edge, N, g, j, lane, on);
+        put(j, col_finish<T, DV, EXACT, ALG>(a, gmsg, post, N, g, j, lane, on));
     }
 }
 
