@@ -46,6 +46,11 @@ def main():
     tr = {}
     for tag in ("row", "col"):
         sel = [x for x in rows if tag + "_pass" in x[idx['Kernel Name']]]
+        # launches of ticks in which the slots were empty (between two waves of a short batch) are not "a launch over
+        # 4096 frames": keep the ones that moved at least half of the largest launch's bytes
+        if sel:
+            top = max(tot(x) for x in sel)
+            sel = [x for x in sel if tot(x) >= 0.5 * top]
         if sel:
             tr[tag] = sum(tot(x) for x in sel) / len(sel)
             tr[tag + "_per_frame"] = tr[tag] / frames
