@@ -127,7 +127,7 @@ def run_reference(args):
                                    % (info["frames"], args.ref_frames_per_core, args.max_iter, args.eps, info["ms_per_iter_per_core"])},
         "e2e": {"value": v, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, frames):
@@ -150,7 +150,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the decoder has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -297,12 +297,32 @@ def run_ours(args):
                 "steps": e2e_steps, "matches_device_path": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on fd 1 when
+    NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the line goes to a private
+    duplicate of the original stdout."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
