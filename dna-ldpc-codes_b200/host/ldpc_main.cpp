@@ -24,7 +24,9 @@
 #include <ctime>
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dnaldpc.h"
@@ -165,24 +167,9 @@ int main(int argc, char **argv) {
     time_t t_start, t_end;
     time(&t_start);
 
-    // LDPC_Encode (DNA_main.cpp:1319-1348): codeword + LLR text, LR = exp(LLR) with the host libm
-    std::vector<signed char> codewords(F * (size_t)N);
-    std::vector<double> llr(F * (size_t)N), lr(F * (size_t)N);
-    std::string err;
-    for (size_t f = 0; f < F; f++) {
-        std::vector<signed char> cw;
-        std::vector<double> l;
-        if (!read_codeword_txt(frames[f].first + ".txt", N, cw, err) || !read_llr_txt(frames[f].second + ".txt", N, l, err)) {
-            fprintf(stderr, "%s\n", err.c_str());
-            return 1;
-        }
-        memcpy(&codewords[f * (size_t)N], cw.data(), (size_t)N);
-        memcpy(&llr[f * (size_t)N], l.data(), (size_t)N * sizeof(double));
-    }
-    for (size_t i = 0; i < lr.size(); i++) lr[i] = exp(llr[i]);
-
-    // A one-frame run is dominated by CUDA initialisation; exposing only the requested GPU to the driver keeps it from
-    // initialising every device of an 8-GPU box (the variable is only set when the caller has not set it).
+    // CUDA context creation dominates a one-process run (about a second); it runs on its own thread while the input
+    // text is parsed. A one-frame run is dominated by it anyway; exposing only the requested GPU to the driver keeps it
+    // from initialising every device of an 8-GPU box (the variable is only set when the caller has not set it).
     {
         char dev[16];
         snprintf(dev, sizeof(dev), "%d", a.device);
@@ -194,9 +181,53 @@ int main(int argc, char **argv) {
     cfg.precision = a.fp32 ? DNALDPC_PREC_F32 : DNALDPC_PREC_F64;
     cfg.wave_frames = (int)std::min<size_t>(4096, (F + 31) / 32 * 32);
     dnaldpc_decoder *dec = nullptr;
+    int create_rc = 0;
+    std::string create_err;
     auto i0 = std::chrono::steady_clock::now();
-    check(dnaldpc_decoder_create(code, &cfg, &dec));  // includes CUDA context creation (dominates a one-frame run)
-    auto i1 = std::chrono::steady_clock::now();
+    std::chrono::steady_clock::time_point i1;
+    std::thread creator([&]() {
+        create_rc = dnaldpc_decoder_create(code, &cfg, &dec);  // includes CUDA context creation
+        if (create_rc) create_err = dnaldpc_last_error();      // thread-local message: keep it before the thread ends
+        i1 = std::chrono::steady_clock::now();
+    });
+
+    // LDPC_Encode (DNA_main.cpp:1319-1348): codeword + LLR text, LR = exp(LLR) with the host libm; frames in parallel
+    std::vector<signed char> codewords(F * (size_t)N);
+    std::vector<double> llr(F * (size_t)N), lr(F * (size_t)N);
+    std::string err;
+    {
+        const unsigned nthr = (unsigned)std::max<size_t>(1, std::min<size_t>({F, (size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16}));
+        std::atomic<size_t> next{0};
+        std::atomic<long> first_bad{-1};
+        std::vector<std::string> errs(F);
+        auto work = [&]() {
+            for (size_t f = next++; f < F; f = next++) {
+                std::vector<signed char> cw;
+                std::vector<double> l;
+                if (!read_codeword_txt(frames[f].first + ".txt", N, cw, errs[f]) || !read_llr_txt(frames[f].second + ".txt", N, l, errs[f])) {
+                    long expect = -1;
+                    first_bad.compare_exchange_strong(expect, (long)f);
+                    continue;
+                }
+                memcpy(&codewords[f * (size_t)N], cw.data(), (size_t)N);
+                memcpy(&llr[f * (size_t)N], l.data(), (size_t)N * sizeof(double));
+                for (int j = 0; j < N; j++) lr[f * (size_t)N + j] = exp(l[(size_t)j]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthr; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        if (first_bad >= 0) {
+            size_t bad = 0;  // report the first frame of the list that failed, like a serial reader would
+            while (errs[bad].empty()) bad++;
+            creator.join();
+            fprintf(stderr, "%s\n", errs[bad].c_str());
+            return 1;
+        }
+    }
+    creator.join();
+    if (create_rc) { fprintf(stderr, "%s\n", create_err.c_str()); return 1; }
 
     std::vector<unsigned char> dblk(F * (size_t)N), okflag(F);
     std::vector<int32_t> iters(F);
