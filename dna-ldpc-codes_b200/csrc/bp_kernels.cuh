@@ -201,6 +201,45 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Arithmetic of one (check, slot) whose DC inputs sit in the lane's column of a shared-memory tile (col[k * 32]):
+// pass 1, descending: d_k in place, backward products check-pointed every 8 edges; pass 2: lr_k streamed to `base`.
+template <typename T, int DC>
+__device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_lane, const int32_t *cols, bool fresh) {
+    constexpr int NB = (DC + 7) / 8;
+    T ck[NB];
+    T B = T(1);
+    bool bad = false;
+#pragma unroll
+    for (int k = DC - 1; k >= 0; k--) {
+        const T dk = check_factor(col[k * kFG], bad);
+        col[k * kFG] = dk;
+        if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
+        B = mul_rn(B, dk);
+    }
+    if (bad) {  // invalid likelihood ratios: nothing stored to msg yet, redo with full IEEE divisions
+        row_slow_path<T>(base, lr_lane, cols, DC, fresh);
+        return;
+    }
+    T F = T(1);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int bot = b * 8;
+        const int top = (bot + 7 < DC - 1) ? bot + 7 : DC - 1;
+        T d[8], Bv[8];
+#pragma unroll
+        for (int k = bot; k <= top; k++) d[k - bot] = col[k * kFG];
+        Bv[top - bot] = ck[b];
+#pragma unroll
+        for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
+#pragma unroll
+        for (int k = bot; k <= top; k++) {
+            const T t = mul_rn(F, Bv[k - bot]);
+            st_stream(base + (size_t)k * kFG, check_to_bit(t));
+            F = mul_rn(F, d[k - bot]);
+        }
+    }
+}
+
 // Check pass with the check's 72 x 32 messages staged in shared memory (regular codes): ONE 18 KB cp.async.bulk per
 // warp lands the contiguous run in the warp's tile, the factors d_k overwrite the tile in place, and only the 9
 // check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
@@ -250,40 +289,7 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    // pass 1, descending: d_k in place, backward products check-pointed every 8 edges
-    constexpr int NB = (DC + 7) / 8;
-    T ck[NB];
-    T B = T(1);
-    bool bad = false;
-#pragma unroll
-    for (int k = DC - 1; k >= 0; k--) {
-        const T dk = check_factor(col[k * kFG], bad);
-        col[k * kFG] = dk;
-        if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
-        B = mul_rn(B, dk);
-    }
-    if (bad) {  // invalid likelihood ratios: nothing stored to msg yet, redo with full IEEE divisions
-        row_slow_path<T>(base, lr_lane, col_idx + e0, DC, fresh);
-        return;
-    }
-    T F = T(1);
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const int bot = b * 8;
-        const int top = (bot + 7 < DC - 1) ? bot + 7 : DC - 1;
-        T d[8], Bv[8];
-#pragma unroll
-        for (int k = bot; k <= top; k++) d[k - bot] = col[k * kFG];
-        Bv[top - bot] = ck[b];
-#pragma unroll
-        for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
-#pragma unroll
-        for (int k = bot; k <= top; k++) {
-            const T t = mul_rn(F, Bv[k - bot]);
-            st_stream(base + (size_t)k * kFG, check_to_bit(t));
-            F = mul_rn(F, d[k - bot]);
-        }
-    }
+    smem_row_compute<T, DC>(col, base, lr_lane, col_idx + e0, fresh);
 }
 
 // ------------------------------------------------------------------------------------------------
