@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "bp_kernels.cuh"
 #include "sw_kernels.cuh"
@@ -449,10 +450,20 @@ int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const 
         dnaldpc_input w = in;
         if (host_exp) {  // LR = exp(LLR) with the host libm, like LDPC_Encode (DNA_main.cpp:1344)
             h_exp_.resize((size_t)nf * N_);
-            for (int64_t f = 0; f < nf; f++) {
-                const double *row = (const double *)(src + (size_t)f * stride);
-                const double sc = in.param == 0.0 ? 1.0 : in.param;
-                for (int j = 0; j < N_; j++) h_exp_[(size_t)f * N_ + j] = std::exp(sc == 1.0 ? row[j] : sc * row[j]);
+            const double sc = in.param == 0.0 ? 1.0 : in.param;
+            auto exp_rows = [&](int64_t fa, int64_t fb) {
+                for (int64_t f = fa; f < fb; f++) {
+                    const double *row = (const double *)(src + (size_t)f * stride);
+                    for (int j = 0; j < N_; j++) h_exp_[(size_t)f * N_ + j] = std::exp(sc == 1.0 ? row[j] : sc * row[j]);
+                }
+            };
+            // libm exp is ~20 ns per value: a large batch is split over the host cores (same libm, same results)
+            const int nthr = (int)std::min<int64_t>({(int64_t)std::max(1u, std::thread::hardware_concurrency()), (int64_t)32, nf / 8 + 1});
+            if (nthr <= 1) exp_rows(0, nf);
+            else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nthr; t++) th.emplace_back(exp_rows, nf * t / nthr, nf * (t + 1) / nthr);
+                for (auto &t : th) t.join();
             }
             CK(cudaMemcpyAsync(s_in_, h_exp_.data(), (size_t)nf * packed, cudaMemcpyHostToDevice, st));
             w.kind = DNALDPC_IN_LR_F64;

@@ -173,3 +173,51 @@ def test_fp32_mode_matches_fer(code, cws):
     assert b["ok"].all() and np.array_equal(b["bits"], tx)
     d64.close()
     d32.close()
+
+
+def test_config2_full_size_properties(code, orc, cws):
+    """configs[1] at its full size: a 100 000-frame batch on one GPU, device-resident, through properties that do not
+    need the oracle on every frame: (1) encode -> BSC(eps) -> decode round trip: every frame flagged as a codeword equals
+    the sent codeword (eps = 0.005, well below the waterfall, and eps = 0.0075 where a few per cent fail); (2) a frame is
+    flagged exactly when its iteration count stayed below max_iter or its last syndrome was zero; (3) the result does not
+    depend on how the frames flow through the slots: a second run with a quarter of the slots (so different refill,
+    drain-tail compaction and kernel-variant decisions) gives identical bits, counts and flags; (4) a sample of frames,
+    stragglers included, against the oracle."""
+    import torch
+    N, W, F, mi = 18432, 576, 100000, 60
+    cw_packed = np.packbits(cws.astype(np.uint8), axis=1, bitorder="little").view(np.uint32)
+    d_cw = torch.from_numpy(cw_packed.astype(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    big = ldpc.Decoder(code, wave_frames=4096)
+    small = ldpc.Decoder(code, wave_frames=1024)
+    for eps, seed in ((0.005, 31), (0.0075, 32)):
+        d_in = torch.empty((F, W), dtype=torch.int32, device="cuda")
+        big.synth_bsc_device(d_cw.data_ptr(), 272, seed, 0, F, eps, d_in.data_ptr(), st)
+        outs = []
+        for dec in (big, small):
+            d_bits = torch.empty((F, W), dtype=torch.int32, device="cuda")
+            d_it = torch.empty(F, dtype=torch.int32, device="cuda")
+            d_ok = torch.empty(F, dtype=torch.uint8, device="cuda")
+            dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), F, mi, param=eps, bits_ptr=d_bits.data_ptr(),
+                              iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=st)
+            torch.cuda.synchronize()
+            outs.append((d_bits, d_it, d_ok))
+        (b0, i0, k0), (b1, i1, k1) = outs
+        assert torch.equal(b0, b1) and torch.equal(i0, i1) and torch.equal(k0, k1), eps          # (3)
+        sent = d_cw[torch.arange(F, device="cuda") % 272]
+        okm = k0.bool()
+        assert torch.equal(b0[okm], sent[okm]), eps                                             # (1)
+        assert bool((i0[~okm] == mi).all()) and bool((i0 >= 1).all()) and bool((i0 <= mi).all())  # (2)
+        fer = 1.0 - float(okm.float().mean())
+        assert (fer < 1e-3) if eps == 0.005 else (0.005 < fer < 0.5), (eps, fer)
+        it = i0.cpu().numpy()
+        bits = b0.cpu().numpy().view(np.uint32)
+        sample = list(range(0, F, 9973)) + list(np.nonzero(it == mi)[0][:3]) + [int(np.argmax(np.where(it < mi, it, 0)))]
+        for f in sample:                                                                         # (4)
+            f = int(f)
+            e = eps
+            lr = np.where((cws[f % 272] ^ ol.bsc_flips(seed, f, N, eps)) == 0, (1 - e) / e, e / (1 - e))
+            o = orc.decode(lr, mi, want_post=False)
+            assert it[f] == o["n"] and int(k0[f]) == o["ok"], (eps, f)
+            assert np.array_equal(bits[f], np.packbits(o["dblk"].astype(np.uint8), bitorder="little").view(np.uint32)), (eps, f)
+    big.close(); small.close()
