@@ -91,3 +91,27 @@ def test_no_cpu_fallback():
     with pytest.raises(ldpc.LdpcError) as ei:
         ldpc.Decoder(code)
     assert ei.value.rc == 4 and "no CPU fallback" in str(ei.value)
+
+
+def test_cli_argument_errors_without_gpu(tmp_path):
+    """The CLI's argument / input-file errors come before any CUDA call: the reference's `argc error!` (DNA_main.cpp:494-502)
+    for a wrong argument count, incl. the sliding-window block of decoder type 60 (:424-429), unsupported decoder types,
+    an unreadable .pchk (rcode.cpp:60-64) and a missing node-count file."""
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "dna-ldpc-codes_b200", "ldpc")
+    d = str(tmp_path)
+    shutil.copyfile(os.path.join(ol.GOLDEN, "sc_z32_l12.pchk"), os.path.join(d, "sc.pchk"))
+
+    def run(*a):
+        return subprocess.run([exe] + list(a), cwd=d, capture_output=True, text=True)
+    r = run("0", "0", "0", "7", "200", "1", "cw", "soft", "sc", "0", "0", "0")            # one argument short
+    assert r.returncode == 1 and "argc error!" in r.stderr
+    r = run("0", "60", "0", "7", "20", "1", "cw", "soft", "sc", "0", "0", "0", "0")       # type 60 without its block
+    assert r.returncode == 1 and "argc error!" in r.stderr
+    r = run("0", "60", "0", "7", "20", "1", "cw", "soft", "sc", "0", "0", "0", "0", "0", "3", "12", "4")
+    assert r.returncode == 1 and "Can't open node-count file: sc.txt" in r.stderr
+    r = run("0", "50", "0", "7", "20", "1", "cw", "soft", "sc", "0", "0", "0", "0")
+    assert r.returncode == 1 and "not supported" in r.stderr
+    r = run("0", "0", "0", "7", "20", "1", "cw", "soft", "nosuch", "0", "0", "0", "0")
+    assert r.returncode == 1 and "nosuch.pchk" in r.stderr
