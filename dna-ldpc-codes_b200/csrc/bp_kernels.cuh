@@ -203,21 +203,26 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 
 // Arithmetic of one (check, slot) whose DC inputs sit in the lane's column of a shared-memory tile (col[k * 32]):
 // pass 1, descending: d_k in place, backward products check-pointed every 8 edges; pass 2: lr_k streamed to `base`.
-template <typename T, int DC>
-__device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_lane, const int32_t *cols, bool fresh) {
+// EXACT = false: rows of any degree deg <= DC (irregular codes); the padding edges k >= deg are exact identities in
+// both product chains and are neither read nor stored.
+template <typename T, int DC, bool EXACT = true>
+__device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_lane, const int32_t *cols, bool fresh, int deg = DC) {
     constexpr int NB = (DC + 7) / 8;
     T ck[NB];
     T B = T(1);
     bool bad = false;
 #pragma unroll
     for (int k = DC - 1; k >= 0; k--) {
-        const T dk = check_factor(col[k * kFG], bad);
-        col[k * kFG] = dk;
+        T dk = T(1);
+        if (EXACT || k < deg) {
+            dk = check_factor(col[k * kFG], bad);
+            col[k * kFG] = dk;
+        }
         if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
         B = mul_rn(B, dk);
     }
     if (bad) {  // invalid likelihood ratios: nothing stored to msg yet, redo with full IEEE divisions
-        row_slow_path<T>(base, lr_lane, cols, DC, fresh);
+        row_slow_path<T>(base, lr_lane, cols, deg, fresh);
         return;
     }
     T F = T(1);
@@ -227,14 +232,14 @@ __device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_la
         const int top = (bot + 7 < DC - 1) ? bot + 7 : DC - 1;
         T d[8], Bv[8];
 #pragma unroll
-        for (int k = bot; k <= top; k++) d[k - bot] = col[k * kFG];
+        for (int k = bot; k <= top; k++) d[k - bot] = (EXACT || k < deg) ? col[k * kFG] : T(1);
         Bv[top - bot] = ck[b];
 #pragma unroll
         for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
 #pragma unroll
         for (int k = bot; k <= top; k++) {
             const T t = mul_rn(F, Bv[k - bot]);
-            st_stream(base + (size_t)k * kFG, check_to_bit(t));
+            if (EXACT || k < deg) st_stream(base + (size_t)k * kFG, check_to_bit(t));
             F = mul_rn(F, d[k - bot]);
         }
     }
@@ -245,11 +250,12 @@ __device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_la
 // check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
 // <= 168 registers: 12 warps (3 CTAs, 3 x 73.8 KB of shared memory) per SM instead of 8, i.e. 50 % more bytes in flight.
 // Groups with a slot that starts a frame or with idle slots fill the tile lane by lane with cp.async instead.
-template <typename T, int DC>
-__global__ void __launch_bounds__(kRowWarps * 32, 3)
+// EXACT = false (irregular rows of degree <= DC): the bulk copy takes the row's deg x 256 bytes; the tile stays DC rows.
+template <typename T, int DC, bool EXACT = true>
+__global__ void __launch_bounds__(kRowWarps * 32, EXACT ? 3 : 6)
 row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
-                     int g0, int G) {
+                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr,
+                     const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
@@ -262,7 +268,8 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
     if (act == 0) return;
     const uint32_t fw = freshw[g];
     const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
-    const int e0 = i * DC;
+    const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
+    const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
     T *base = msg + ((size_t)g * E + e0) * kFG + lane;
     T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
     const T *lr_lane = lratio + (size_t)g * N * kFG + lane;
@@ -270,8 +277,8 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
         if (lane == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
-            mbar_expect_tx(bar, (uint32_t)(DC * kFG * sizeof(T)));
-            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(DC * kFG * sizeof(T)), bar);
+            mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
+            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar);
         }
         __syncwarp();
         mbar_wait(bar, 0);
@@ -283,13 +290,14 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
         if (!on) return;
 #pragma unroll 12
         for (int k = 0; k < DC; k++) {
+            if (!EXACT && k >= deg) break;
             const T *src = fresh ? lr_lane + (size_t)__ldg(col_idx + e0 + k) * kFG : base + (size_t)k * kFG;
             asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(col + k * kFG)), "l"(src), "n"(sizeof(T)) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    smem_row_compute<T, DC>(col, base, lr_lane, col_idx + e0, fresh);
+    smem_row_compute<T, DC, EXACT>(col, base, lr_lane, col_idx + e0, fresh, deg);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -151,7 +151,11 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
             CK(cudaFuncSetAttribute(row_pass_smem_kernel<T, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        row_pass_smem_kernel<T, 72><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G);
+        row_pass_smem_kernel<T, 72><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);
+    } else if (!no_smem && (steady_ || always_smem) && max_row_deg_ <= 32 && max_row_deg_ > 8 && !minsum_ && sizeof(T) == 8) {
+        // irregular rows of degree <= 32 (e.g. the n=65536 column-weight-3 code): same staging, deg x 256 B bulk copies
+        const size_t smem = (size_t)kRowWarps * 32 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
+        row_pass_smem_kernel<T, 32, false><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);
     } else if (reg_rows_ && max_row_deg_ == 72) ROW(72, true);
     else if (max_row_deg_ <= 8) ROW(8, false);
     else if (max_row_deg_ <= 32) ROW(32, false);
