@@ -255,8 +255,11 @@ int main(int argc, char **argv) {
     for (size_t f = 0; f < F; f++) {
         long long raw = 0, dec_err = 0;
         for (int i = 0; i < len; i++) {
-            const int hard = llr[f * (size_t)N + i] >= 0 ? 0 : 1;
-            raw += (codewords[f * (size_t)N + i] != hard);
+            // channel type 0 compares the sign of the soft input; types 1 / 2 look at g_recv_codeword_hard, which nothing
+            // fills since the channel simulators are commented out (DNA_main.cpp:1358-1371): calloc'ed zeros, i.e.
+            // "received 0" for the BSC branch and "nothing erased" for the BEC branch (:1733-1745)
+            const int hard = a.channel_type == 0 ? (llr[f * (size_t)N + i] >= 0 ? 0 : 1) : 0;
+            if (a.channel_type != 2) raw += (codewords[f * (size_t)N + i] != hard);
             dec_err += (codewords[f * (size_t)N + i] != (signed char)dblk[f * (size_t)N + i]);
         }
         bit_err[0] += raw; frame_err[0] += raw > 0;

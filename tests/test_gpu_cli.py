@@ -134,3 +134,33 @@ def test_cli_sliding_window_side_by_side(tmp_path):
         outs[who] = (r.stdout, open(os.path.join(d, "dec_cw.txt"), "rb").read(), res[0], [l for l in body if not l.startswith("BER[")])
     assert outs["ours"] == outs["ref"]
     assert len(g["Mv"]) == D
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ldpc_ref not built")
+@pytest.mark.parametrize("args", [
+    ("1", "0", "1", "7", "20", "3", "cw", "soft", "sc", "0.05", "0", "0", "0"),    # systematic count, BSC naming (%.4f), frame_num 3
+    ("0", "0", "2", "5", "10", "1", "cw", "soft", "sc", "0.3", "0", "0", "0"),     # BEC naming / "Eps" lines
+    ("0", "21", "0", "9", "15", "2", "cw", "soft", "sc", "1.5", "0", "0", "0"),    # min-sum type 21, Eb/N0 1.5 dB -> g_std_dev
+    ("0", "0", "0", "7", "0", "1", "cw", "soft", "sc", "0", "0", "0", "0"),        # max_iter 0
+])
+def test_cli_argument_variants_side_by_side(tmp_path, args):
+    """The positional arguments the pipeline never varies (bSystematic, channel type + parameter, frame_num, seed,
+    max_iter 0) against the unmodified reference CLI on the small SC code: stdout, dec file, result-file name and body."""
+    N = 768
+    rs = np.random.RandomState(12)
+    llr = np.where(rs.rand(N) < 0.04, -1.0, 1.0) * rs.uniform(0.5, 4.0, N)
+    outs = {}
+    for who, exe in (("ours", LDPC), ("ref", REF_CLI)):
+        d = str(tmp_path / who)
+        os.makedirs(d)
+        shutil.copyfile(os.path.join(ol.GOLDEN, "sc_z32_l12.pchk"), os.path.join(d, "sc.pchk"))
+        with open(os.path.join(d, "cw.txt"), "w") as fh:
+            fh.write("0 " * N)
+        with open(os.path.join(d, "soft.txt"), "w") as fh:
+            fh.write(" ".join(repr(float(x)) for x in llr))
+        r = subprocess.run([exe] + list(args), cwd=d, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        res = [f for f in os.listdir(d) if f.startswith("result_")]
+        assert len(res) == 1
+        outs[who] = (r.stdout, open(os.path.join(d, "dec_cw.txt"), "rb").read(), res[0], _strip_times(open(os.path.join(d, res[0])).read()))
+    assert outs["ours"] == outs["ref"]
