@@ -308,6 +308,9 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
     // region are still busy they are compacted into the lowest groups (compact_*_kernel) and the check / bit passes
     // shrink to those groups.
     const bool no_compact = getenv("DNALDPC_NO_COMPACT") != nullptr;  // A/B switch, read per batch
+    // threshold in per cent of the packed region (default kCompactNum / kCompactDen = 50); tests raise it to make the
+    // batch compact at almost every tick
+    const long long compact_pct = getenv("DNALDPC_COMPACT_PCT") ? std::max(1, std::min(99, atoi(getenv("DNALDPC_COMPACT_PCT")))) : 100LL * kCompactNum / kCompactDen;
     long long admitted_total = 0;
     int G_rc = G;                             // groups the check / bit passes are launched over
     long long packed_cap = (long long)G * kFG;  // slots of the region the busy slots were last packed into
@@ -348,7 +351,7 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
             steady_ = last_admitted == 0 && last_busy >= (unsigned)G * kFG;
             admitted_total += last_admitted;
             if (!no_compact && !profiling && admitted_total >= F && packed_cap >= 2 * kFG &&
-                (long long)last_busy * kCompactDen <= packed_cap * kCompactNum) {
+                (long long)last_busy * 100 <= packed_cap * compact_pct) {
                 // `last_busy` is kLag ticks old and can only have shrunk since: it bounds the moves and the packed size
                 int32_t *mv_src = d_mv_, *mv_dst = d_mv_ + (size_t)cap_groups_ * kFG, *mv_cnt = d_mv_ + (size_t)cap_groups_ * kFG * 2;
                 compact_plan_kernel<<<1, 32, 0, st>>>(s, G, mv_src, mv_dst, mv_cnt);

@@ -451,6 +451,42 @@ def test_sliding_window_decoder():
     dec.close()
 
 
+def test_compaction_stress_small_code():
+    """Drain-tail compaction forced at almost every tick (threshold raised to 97 % of the packed region through the test
+    switch): slots are moved again and again, next to slots that wait for their harvest, with posteriors and syndromes
+    requested, for sum-product and min-sum. Every frame against the oracle on the small code."""
+    path = os.path.join(ol.GOLDEN, "small_n120_m60.pchk")
+    code = ldpc.Code(path)
+    orc = ol.Oracle(path)
+    rs = np.random.RandomState(77)
+    Nn = 120
+    os.environ["DNALDPC_COMPACT_PCT"] = "97"
+    try:
+        total = 0
+        for wave, F, mi in [(256, 256, 40), (512, 700, 25), (128, 128, 60)]:
+            dec = ldpc.Decoder(code, wave_frames=wave)
+            q = rs.choice([0.02, 0.05, 0.08, 0.12], size=F)
+            flips = rs.rand(F, Nn) < q[:, None]
+            llr = np.where(flips, -1.0, 1.0) * rs.uniform(0.5, 5.0, (F, Nn))
+            lr = np.exp(llr)
+            r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=("bits", "iters", "ok", "post", "pchk"))
+            total += dec.stats()["compactions"]
+            m = dec.decode(ldpc.IN_LLR_F64, llr, mi, flags=ldpc.FLAG_MINSUM, want=("bits", "iters", "ok", "post"))
+            total += dec.stats()["compactions"]
+            for f in range(F):
+                o = orc.decode(lr[f], mi)
+                assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (wave, F, f)
+                assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (wave, F, f)
+                assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, F, f)
+                o = orc.decode_minsum(llr[f], mi)
+                assert m["iters"][f] == o["n"] and m["ok"][f] == o["ok"] and np.array_equal(m["bits"][f], o["dblk"]), (wave, F, f)
+                assert np.array_equal(m["post"][f].view(np.uint64), o["post"].view(np.uint64)), (wave, F, f)
+            dec.close()
+        assert total >= 12, total
+    finally:
+        del os.environ["DNALDPC_COMPACT_PCT"]
+
+
 def test_smem_check_kernel_mixed_groups_in_subprocess():
     """The shared-memory check kernel normally runs only in the steady state (full groups, nobody admitted). Its
     cp.async path for mixed groups (fresh / idle lanes) is forced here with the A/B switch, in a child process
