@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Randomised campaign of the GPU decoder (through the C ABI) against the CPU oracle on the small N=120 code, where the
+oracle is cheap: random batch sizes, slot counts, iteration caps, input classes, sum-product and min-sum; every frame's
+n, success flag, decoded bits, syndrome and posterior bit for bit. Exercises the slot scheduler (admission, two-round
+refill, drain-tail compaction, kernel-variant choices) far beyond the test suite. Needs a GPU.
+
+  fuzz_gpu_vs_oracle.py SECONDS
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import _pkg  # noqa: E402
+import oraclelib as ol  # noqa: E402
+from fuzz_oracle_vs_ref import ratios  # noqa: E402
+
+
+def main():
+    seconds = float(sys.argv[1])
+    ldpc = _pkg.load()
+    path = os.path.join(ol.GOLDEN, "small_n120_m60.pchk")
+    code, orc = ldpc.Code(path), ol.Oracle(path)
+    N = code.N
+    rs = np.random.RandomState(99)
+    t0, frames, batches, comp = time.time(), 0, 0, 0
+    decs = {}
+    while time.time() - t0 < seconds:
+        wave = int(rs.choice([32, 64, 96, 256, 1024, 4096]))
+        F = int(rs.choice([1, 31, 33, 100, 700, 3000, 9000]))
+        mi = int(rs.choice([0, 1, 4, 20, 60, 200]))
+        dec = decs.get(wave) or decs.setdefault(wave, ldpc.Decoder(code, wave_frames=wave))
+        q = rs.choice([0.0, 0.02, 0.05, 0.08, 0.12, 0.2], size=F)
+        kinds = rs.randint(0, 4, size=F)
+        lr = np.stack([ratios(rs, N, q[f], kinds[f]) for f in range(F)])
+        r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=("bits", "iters", "ok", "post", "pchk"))
+        comp += dec.stats()["compactions"]
+        llr = np.log(np.maximum(lr, 1e-300))
+        llr = np.where(np.isfinite(llr), llr, 700.0)
+        m = dec.decode(ldpc.IN_LLR_F64, llr, mi, flags=ldpc.FLAG_MINSUM, want=("bits", "iters", "ok", "post"))
+        comp += dec.stats()["compactions"]
+        for f in range(F):
+            o = orc.decode(lr[f], mi)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], ("bp", wave, F, mi, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), ("bp", wave, F, mi, f)
+            assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), ("bp post", wave, F, mi, f)
+            o = orc.decode_minsum(llr[f], mi)
+            assert m["iters"][f] == o["n"] and m["ok"][f] == o["ok"] and np.array_equal(m["bits"][f], o["dblk"]), ("ms", wave, F, mi, f)
+            assert np.array_equal(m["post"][f].view(np.uint64), o["post"].view(np.uint64)), ("ms post", wave, F, mi, f)
+        frames += F
+        batches += 1
+    print("GPU vs oracle: %d batches, %d frames x 2 algorithms identical; %d compactions" % (batches, frames, comp))
+
+
+if __name__ == "__main__":
+    main()
