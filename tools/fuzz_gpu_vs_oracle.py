@@ -4,7 +4,8 @@ oracle is cheap: random batch sizes, slot counts, iteration caps, input classes,
 n, success flag, decoded bits, syndrome and posterior bit for bit. Exercises the slot scheduler (admission, two-round
 refill, drain-tail compaction, kernel-variant choices) far beyond the test suite. Needs a GPU.
 
-  fuzz_gpu_vs_oracle.py SECONDS
+  fuzz_gpu_vs_oracle.py SECONDS        flooding sum-product + min-sum, small code
+  fuzz_gpu_vs_oracle.py SECONDS sw     sliding-window BP on the SC-LDPC code (window 1..14, code_type 0 / 1)
 """
 import os
 import sys
@@ -21,8 +22,39 @@ import oraclelib as ol  # noqa: E402
 from fuzz_oracle_vs_ref import ratios  # noqa: E402
 
 
+def main_sw(seconds):
+    import gen_sc_pchk
+    ldpc = _pkg.load()
+    path = os.path.join(ol.GOLDEN, "sc_z32_l12.pchk")
+    _, N, _, _, Mv, Mc = gen_sc_pchk.gen_sc(32, 12, 11)
+    code, orc = ldpc.Code(path), ol.Oracle(path)
+    rs = np.random.RandomState(5)
+    decs = {}
+    t0, frames, batches = time.time(), 0, 0
+    while time.time() - t0 < seconds:
+        wave = int(rs.choice([32, 64, 256]))
+        F = int(rs.choice([1, 33, 100, 300]))
+        ct = int(rs.randint(0, 2))
+        D = 12 + 3 - 1 if ct == 0 else 12 + (3 - 1) // 2
+        win, mi = min(int(rs.randint(1, 15)), D), int(rs.choice([0, 1, 2, 5, 12, 40]))
+        dec = decs.get(wave) or decs.setdefault(wave, ldpc.Decoder(code, wave_frames=wave))
+        q = rs.choice([0.0, 0.02, 0.04, 0.06, 0.08, 0.1, 0.15], size=F)
+        kinds = rs.randint(0, 3, size=F)
+        lr = np.stack([ratios(rs, N, q[f], kinds[f]) for f in range(F)])
+        r = dec.decode_window(lr, mi, 12, 3, win, Mv[:D], Mc[:D], code_type=ct, want=("bits", "iters", "ok", "pchk"))
+        for f in range(F):
+            o = orc.decode_sw(lr[f], mi, 12, 3, win, Mv[:D], Mc[:D], code_type=ct)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (wave, F, win, mi, ct, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (wave, F, win, mi, ct, f)
+        frames += F
+        batches += 1
+    print("GPU sliding window vs oracle: %d batches, %d frames identical" % (batches, frames))
+
+
 def main():
     seconds = float(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "sw":
+        return main_sw(seconds)
     ldpc = _pkg.load()
     path = os.path.join(ol.GOLDEN, "small_n120_m60.pchk")
     code, orc = ldpc.Code(path), ol.Oracle(path)
