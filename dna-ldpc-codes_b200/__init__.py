@@ -26,6 +26,7 @@ EXPORTS = [
     "dnaldpc_decode_batch_device", "dnaldpc_run_bp_decoder", "dnaldpc_std_dev", "dnaldpc_vote_table",
     "dnaldpc_bsc_table", "dnaldpc_synth_bsc_device", "dnaldpc_get_stats", "dnaldpc_set_profiling",
     "dnaldpc_selftest_math", "dnaldpc_redecode_sweep", "dnaldpc_get_trace", "dnaldpc_decode_window",
+    "dnaldpc_redecode_sweep_ex", "dnaldpc_synth_awgn_device", "dnaldpc_synth_vote_device",
 ]
 
 
@@ -100,6 +101,12 @@ def lib():
         L.dnaldpc_get_trace.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.dnaldpc_redecode_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.POINTER(Output), C.c_void_p]
+        L.dnaldpc_redecode_sweep_ex.argtypes = [C.c_void_p, C.POINTER(Input), C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                                                C.POINTER(Output), C.c_void_p]
+        L.dnaldpc_synth_awgn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64,
+                                                C.c_double, C.c_void_p, C.c_void_p]
+        L.dnaldpc_synth_vote_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64,
+                                                C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.dnaldpc_decode_window.argtypes = [C.c_void_p, C.POINTER(Window), C.c_void_p, C.c_int64, C.c_int, C.POINTER(Output)]
         _lib = L
     return _lib
@@ -220,6 +227,33 @@ class Decoder:
                                     bitorder="little")[:, :N].astype(np.int8)
         return res
 
+    def redecode_sweep_ex(self, kind, data, max_iter, params, flags=0, want=("bits", "iters", "ok")):
+        """The sweep for any parameterised input kind: round r decodes with param = params[r]; inputs stay in HBM."""
+        N, M = self.code.N, self.code.M
+        data = np.ascontiguousarray(data, dtype=_KIND_DTYPE[kind])
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        F = data.shape[0]
+        inp = Input(kind=kind, flags=flags, data=data.ctypes.data, frame_stride=0, param=float(params[0]), table=None)
+        res, out = dict(rounds=np.zeros(F, np.int32)), Output()
+        if "bits" in want:
+            res["bits_packed"] = np.zeros((F, self.words_per_frame), np.uint32); out.bits = res["bits_packed"].ctypes.data
+        if "dblk" in want:
+            res["dblk"] = np.zeros((F, N), np.uint8); out.dblk = res["dblk"].ctypes.data
+        if "iters" in want:
+            res["iters"] = np.zeros(F, np.int32); out.iters = res["iters"].ctypes.data
+        if "ok" in want:
+            res["ok"] = np.zeros(F, np.uint8); out.is_codeword = res["ok"].ctypes.data
+        if "post" in want:
+            res["post"] = np.zeros((F, N), np.float64); out.posterior = res["post"].ctypes.data
+        if "pchk" in want:
+            res["pchk"] = np.zeros((F, M), np.uint8); out.pchk = res["pchk"].ctypes.data
+        _check(lib().dnaldpc_redecode_sweep_ex(self._h, C.byref(inp), F, max_iter, params.ctypes.data, len(params),
+                                               C.byref(out), res["rounds"].ctypes.data))
+        if "bits" in want:
+            res["bits"] = np.unpackbits(res["bits_packed"].view(np.uint8).reshape(F, self.words_per_frame * 4), axis=1,
+                                        bitorder="little")[:, :N].astype(np.int8)
+        return res
+
     def decode_window(self, lratio, max_iter, L, w, win, Mv, Mc, code_type=0, want=("bits", "iters", "ok")):
         """Sliding-window BP for SC-LDPC codes (Run_SW_Decoder, dec.cpp:2092-2196). lratio: [F][N] p0/p1."""
         N, M = self.code.N, self.code.M
@@ -254,14 +288,22 @@ class Decoder:
         return dict(n=n.value, ok=ok.value, dblk=dblk, pchk=pchk)
 
     def decode_device(self, kind, data_ptr, F, max_iter, param=0.0, bits_ptr=None, iters_ptr=None, ok_ptr=None,
-                      post_ptr=None, dblk_ptr=None, pchk_ptr=None, table_ptr=None, stream=None, frame_stride=0):
-        """DEVICE pointers (ints), asynchronous on `stream` (a cudaStream_t as int, None = default stream)."""
-        inp = Input(kind=kind, flags=0, data=data_ptr, frame_stride=frame_stride, param=param, table=table_ptr)
+                      post_ptr=None, dblk_ptr=None, pchk_ptr=None, table_ptr=None, stream=None, frame_stride=0, flags=0):
+        """DEVICE pointers (ints) of buffers on one GPU; the decoder's first device works on `stream` (a cudaStream_t as
+        int, None = default stream), its other devices reach the buffers through peer access. `table_ptr` may be a host
+        or a device pointer."""
+        inp = Input(kind=kind, flags=flags, data=data_ptr, frame_stride=frame_stride, param=param, table=table_ptr)
         out = Output(bits=bits_ptr, dblk=dblk_ptr, iters=iters_ptr, is_codeword=ok_ptr, posterior=post_ptr, pchk=pchk_ptr)
         _check(lib().dnaldpc_decode_batch_device(self._h, C.byref(inp), F, max_iter, C.byref(out), stream))
 
     def synth_bsc_device(self, cw_bits_ptr, n_cw, seed, frame0, F, eps, out_bits_ptr, stream=None):
         _check(lib().dnaldpc_synth_bsc_device(self._h, cw_bits_ptr, n_cw, seed, frame0, F, eps, out_bits_ptr, stream))
+
+    def synth_awgn_device(self, cw_bits_ptr, n_cw, seed, frame0, F, sigma, out_y_ptr, stream=None):
+        _check(lib().dnaldpc_synth_awgn_device(self._h, cw_bits_ptr, n_cw, seed, frame0, F, sigma, out_y_ptr, stream))
+
+    def synth_vote_device(self, cw_bits_ptr, n_cw, seed, frame0, F, mean_reads, read_err, out_k_ptr, stream=None):
+        _check(lib().dnaldpc_synth_vote_device(self._h, cw_bits_ptr, n_cw, seed, frame0, F, mean_reads, read_err, out_k_ptr, stream))
 
     def stats(self):
         s = Stats()

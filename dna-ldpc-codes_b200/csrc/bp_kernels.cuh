@@ -424,13 +424,36 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
 struct SchedArrays {
     uint32_t *actw, *donew, *newfw, *freshw, *harvw, *unsatw;
     unsigned int *arrive;
-    int32_t *slot_frame, *slot_iter, *harv_frame, *harv_iter;
-    unsigned long long *next_frame;
+    int32_t *slot_frame, *slot_iter, *harv_frame, *harv_iter;  // slot_frame / harv_frame hold the frame's queue position q
+    unsigned long long *next_frame;  // next queue position to admit
+    unsigned long long *avail;       // queue positions published so far: frames q < *avail have their inputs resident
+    const int32_t *in_row, *out_row; // per q: row of the frame in the input / output buffers (written by publish_kernel)
+    unsigned long long *iter_sum;    // += iterations of every frame that finishes (dnaldpc_stats.frame_iters)
 };
 
+// The frame queue. A batch reaches an engine as a sequence of frames q = 0, 1, 2, ... that is PUBLISHED piece by piece
+// while the engine is already decoding: the producer (a copy stream that has just landed a piece of a host batch in the
+// staging ring, or the decode stream itself for device-resident batches) appends the rows of the piece to in_row /
+// out_row and then raises *avail. Admission (assign_kernel) takes frames below *avail only, so host->device copies,
+// decoding and device->host copies of one batch overlap, several GPUs can pull pieces of one batch from a shared
+// counter, and a re-decoding round can run over an arbitrary list of rows (`list`), all with the same kernels.
+// One CTA; the table entries are fenced before the counter moves. Readers use ld.cg (the tables grow while kernels run).
+__global__ void __launch_bounds__(1024)
+publish_kernel(int32_t *__restrict__ in_row, int32_t *__restrict__ out_row, long long q0, int n,
+               const int32_t *__restrict__ list_in, int row0_in, int row0_out, unsigned long long *avail) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        in_row[q0 + i] = list_in ? list_in[i] : row0_in + i;
+        out_row[q0 + i] = row0_out + i;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *((volatile unsigned long long *)avail) = (unsigned long long)(q0 + n);
+}
+
 __global__ void __launch_bounds__(256)
-assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round,
-              unsigned int *admitted /* += frames admitted (the host schedules the next ticks from it) */) {
+assign_kernel(SchedArrays s, int g0, int G, int first_round,
+              unsigned int *admitted /* += frames admitted (the host schedules the next ticks from it) */,
+              unsigned int *low_water /* min= smallest q still in a slot after this admission */) {
     const int lane = threadIdx.x & 31;
     const int gl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gl >= G) return;
@@ -442,21 +465,35 @@ assign_kernel(SchedArrays s, long long F, int g0, int G, int first_round,
     }
     const uint32_t free_mask = ~act;  // finished or empty slots
     const int cnt = __popc(free_mask);
-    long long base = F;
-    if (lane == 0 && cnt > 0) {
-        const unsigned long long cur = *((volatile unsigned long long *)s.next_frame);
-        if ((long long)cur < F) base = (long long)atomicAdd(s.next_frame, (unsigned long long)cnt);
+    long long base = 0;
+    int got = 0;
+    if (lane == 0 && cnt > 0) {  // claim up to cnt of the published, not yet admitted frames
+        unsigned long long cur = *((volatile unsigned long long *)s.next_frame);
+        const unsigned long long av = *((volatile unsigned long long *)s.avail);
+        while (cur < av) {
+            const unsigned long long n = min((unsigned long long)cnt, av - cur);
+            const unsigned long long old = atomicCAS(s.next_frame, cur, cur + n);
+            if (old == cur) { base = (long long)cur; got = (int)n; break; }
+            cur = old;
+        }
     }
     base = __shfl_sync(0xffffffffu, base, 0);
+    got = __shfl_sync(0xffffffffu, got, 0);
     const bool is_free = (free_mask >> lane) & 1u;
-    const long long idx = base + __popc(free_mask & ((1u << lane) - 1u));
-    const bool take = is_free && idx < F;
+    const int rank = __popc(free_mask & ((1u << lane) - 1u));
+    const bool take = is_free && rank < got;
     const uint32_t newf = __ballot_sync(0xffffffffu, take);
-    if (take) { s.slot_frame[slot] = (int32_t)idx; s.slot_iter[slot] = 0; }
+    if (take) { s.slot_frame[slot] = (int32_t)(base + rank); s.slot_iter[slot] = 0; }
     else if (is_free) s.slot_frame[slot] = -1;
+    // everything below the smallest q that still sits in a slot has been harvested (or is being harvested by the
+    // harvest kernel that follows this launch): the host retires output blocks from it
+    const uint32_t inuse = act | newf;
+    const unsigned mine = ((inuse >> lane) & 1u) ? (unsigned)s.slot_frame[slot] : 0xffffffffu;
+    const unsigned lw = __reduce_min_sync(0xffffffffu, mine);
     if (lane == 0) {
         if (newf) atomicAdd(admitted, (unsigned)__popc(newf));
-        s.actw[g] = act | newf;
+        if (lw != 0xffffffffu) atomicMin(low_water, lw);
+        s.actw[g] = inuse;
         s.donew[g] = 0;
         s.newfw[g] = newf;
         s.harvw[g] = done;
@@ -479,28 +516,25 @@ struct SynArgs {
     int32_t *iters_out;
     uint8_t *ok_out;
     int M, N, g0, max_iter, consider_new, fixed_iters;
-    unsigned int *counter;          // [0] += slots still busy (active or awaiting harvest) + pending frames, or NULL when a
-                                    // later launch of the tick counts
+    unsigned int *counter;          // [0] += slots in use (active or awaiting harvest), or NULL when a later launch of
+                                    // the tick counts
     unsigned int *finished;         // += frames that finished in this launch
-    unsigned int *counters_to_zero; // ring entry (3 words) re-armed for a later tick, or NULL
+    unsigned int *counters_to_zero; // ring entry (kCounterWords words) re-armed for a later tick, or NULL
     int clear_fresh;                // tick without admission: no assign_kernel will reset the fresh marks
-    long long F;
 };
+
+constexpr int kCounterWords = 4;    // per tick: slots in use, frames admitted, frames finished, low-water q (armed to ~0)
 
 // Common head: housekeeping + "nothing to examine in this group" (uniform over the CTAs of the group: the masks only
 // change in the last arriver). Returns the mask of slots to examine (0 = this CTA is finished).
 __device__ __forceinline__ uint32_t syn_head(const SchedArrays &s, const SynArgs &a, int g, uint32_t &act) {
     if (a.counters_to_zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        a.counters_to_zero[0] = 0; a.counters_to_zero[1] = 0; a.counters_to_zero[2] = 0;
+        a.counters_to_zero[0] = 0; a.counters_to_zero[1] = 0; a.counters_to_zero[2] = 0; a.counters_to_zero[3] = 0xffffffffu;
     }
     act = s.actw[g];
     const uint32_t consider = a.consider_new ? s.newfw[g] : act;
     if (consider == 0 && a.counter && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned add = (unsigned)(__popc(act) + __popc(s.donew[g]));
-        if (blockIdx.y == 0) {
-            const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
-            if (nx < a.F) add += (unsigned)min(a.F - nx, 1000000000LL);
-        }
+        const unsigned add = (unsigned)(__popc(act) + __popc(s.donew[g]));
         if (add) atomicAdd(a.counter, add);
     }
     return consider;
@@ -535,14 +569,17 @@ __device__ __forceinline__ void syn_tail(const SchedArrays &s, const SynArgs &a,
         // fixed_iters (Run_Belief_Propagation_Decoder_SAVE, dec.cpp:192-223): a zero syndrome does not stop the frame
         const uint32_t done = a.fixed_iters ? (consider & maxed) : ((consider & ~unsat) | (consider & maxed));
         const uint32_t done_ok = done & ~unsat;
-        if ((done >> f) & 1u) {
-            const int fr = s.slot_frame[slot];
-            a.iters_out[fr] = it;
-            a.ok_out[fr] = (uint8_t)((done_ok >> f) & 1u);
+        const bool fin = (done >> f) & 1u;
+        if (fin) {
+            const int row = __ldcg(s.out_row + s.slot_frame[slot]);
+            a.iters_out[row] = it;
+            a.ok_out[row] = (uint8_t)((done_ok >> f) & 1u);
         } else if (mine) {
             s.slot_iter[slot] = it + 1;  // this slot runs one more iteration now
         }
+        const unsigned itsum = __reduce_add_sync(0xffffffffu, fin ? (unsigned)it : 0u);
         if (f == 0) {
+            if (itsum) atomicAdd(s.iter_sum, (unsigned long long)itsum);
             const uint32_t still = act & ~done;
             const uint32_t dn = s.donew[g] | done;
             s.actw[g] = still;
@@ -552,11 +589,7 @@ __device__ __forceinline__ void syn_tail(const SchedArrays &s, const SynArgs &a,
             if (a.clear_fresh) s.freshw[g] = 0;  // every slot admitted earlier has had its first check pass
             if (done) atomicAdd(a.finished, (unsigned)__popc(done));
             if (a.counter) {
-                unsigned add = (unsigned)(__popc(still) + __popc(dn));
-                if (blockIdx.y == 0) {
-                    const long long nx = (long long)*((volatile unsigned long long *)s.next_frame);
-                    if (nx < a.F) add += (unsigned)min(a.F - nx, 1000000000LL);
-                }
+                const unsigned add = (unsigned)(__popc(still) + __popc(dn));
                 if (add) atomicAdd(a.counter, add);
             }
         }
@@ -695,10 +728,11 @@ harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ 
     __shared__ double tiles[kHsWarps][32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double (*tile)[33] = tiles[warp];
-    const int my_new = s.slot_frame[g * kFG + lane];   // lane = slot
-    const int my_old = s.harv_frame[g * kFG + lane];
+    const bool is_new = (nf >> lane) & 1u, is_old = (hv >> lane) & 1u;  // lane = slot
+    // rows of this slot's frames in the caller's (or the staging ring's) input / output buffers
+    const int my_new = is_new ? __ldcg(s.in_row + s.slot_frame[g * kFG + lane]) : 0;
+    const int my_old = is_old ? __ldcg(s.out_row + s.harv_frame[g * kFG + lane]) : 0;
     const int my_oldit = s.harv_iter[g * kFG + lane];
-    const bool is_new = (nf >> lane) & 1u, is_old = (hv >> lane) & 1u;
     const int ntiles = (N + 31) / 32;
     const int t0 = (blockIdx.x * kHsWarps + warp) * kHsTilesPerWarp;
     for (int tile_id = t0; tile_id < min(ntiles, t0 + kHsTilesPerWarp); tile_id++) {
@@ -787,7 +821,7 @@ syndrome_bytes_kernel(const uint32_t *__restrict__ decw, SchedArrays s, const in
     for (int e = __ldg(row_ptr + i); e < e1; e++) p ^= __ldg(dw + __ldg(col_idx + e));
     for (uint32_t m = hv; m; m &= m - 1) {
         const int f = __ffs(m) - 1;
-        out[(size_t)s.harv_frame[g * kFG + f] * M + i] = (uint8_t)((p >> f) & 1u);
+        out[(size_t)__ldcg(s.out_row + s.harv_frame[g * kFG + f]) * M + i] = (uint8_t)((p >> f) & 1u);
     }
 }
 
@@ -874,11 +908,37 @@ compact_move_kernel(T *__restrict__ msg, T *__restrict__ lratio, const int32_t *
     }
 }
 
-__global__ void init_sched_kernel(SchedArrays s, int G) {
+// Rows of the frames a re-decoding round takes (decoder.py:641-660): stable compaction of {k : ok[k] == 0}, one CTA.
+__global__ void __launch_bounds__(1024)
+failed_rows_kernel(const uint8_t *__restrict__ ok, const int32_t *__restrict__ prev_list, int n, int32_t *__restrict__ list_out,
+                   int32_t *__restrict__ count) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += 1024) {
+        const int k = k0 + threadIdx.x;
+        const bool bad = k < n && ok[k] == 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, bad);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; w++) off += warp_cnt[w];
+        if (bad) list_out[off + __popc(m & ((1u << lane) - 1u))] = prev_list ? prev_list[k] : k;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; w++) t += warp_cnt[w]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void init_sched_kernel(SchedArrays s, int G, unsigned int *counters, int n_counter_sets) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < G * kFG) { s.slot_frame[t] = -1; s.slot_iter[t] = 0; s.harv_frame[t] = -1; s.harv_iter[t] = 0; }
     if (t < G) { s.actw[t] = 0; s.donew[t] = 0; s.newfw[t] = 0; s.freshw[t] = 0; s.harvw[t] = 0; s.unsatw[t] = 0; s.arrive[t] = 0; }
-    if (t == 0) *s.next_frame = 0;
+    if (t < n_counter_sets * kCounterWords) counters[t] = (t % kCounterWords == 3) ? 0xffffffffu : 0u;
+    if (t == 0) { *s.next_frame = 0; *s.avail = 0; *s.iter_sum = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -914,6 +974,50 @@ synth_bsc_kernel(const uint32_t *__restrict__ cw_bits, int n_cw, uint64_t seed, 
         }
     }
     out[t] = word;
+}
+
+// Synthetic AWGN input (BASELINE configs[3]; channel_AWGN, channel.cpp:23-35): y = (bit ? -1 : +1) + sigma * n with
+// n ~ N(0,1) by Box-Muller from the counter RNG: u1 = ((rng(seed, f, j, 4) >> 11) + 1) / 2^53 in (0, 1],
+// u2 = (rng(seed, f, j, 5) >> 11) / 2^53, n = sqrt(-2 ln u1) cos(2 pi u2), all in fp64, y rounded to fp32.
+// Host twin: oracle/bp_oracle.c:orc_synth_awgn (libm; agrees to the last fp32 ulp except where the fp64 values
+// straddle a rounding boundary). Keyed by the GLOBAL frame index like synth_bsc_kernel.
+__global__ void __launch_bounds__(256)
+synth_awgn_kernel(const uint32_t *__restrict__ cw_bits, int n_cw, uint64_t seed, long long frame0, long long F, int N,
+                  int words_per_frame, double sigma, float *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * N) return;
+    const long long fl = t / N;
+    const int j = (int)(t - fl * N);
+    const uint64_t f = (uint64_t)(frame0 + fl);
+    const uint32_t bit = cw_bits ? (cw_bits[(size_t)(f % (uint64_t)n_cw) * words_per_frame + (j >> 5)] >> (j & 31)) & 1u : 0u;
+    const double u1 = ((double)(rng_u64(seed, f, (uint64_t)j, 4) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u2 = (double)(rng_u64(seed, f, (uint64_t)j, 5) >> 11) * (1.0 / 9007199254740992.0);
+    const double n = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+    out[t] = (float)((bit ? -1.0 : 1.0) + sigma * n);
+}
+
+// Synthetic vote-count input (BASELINE configs[2]; the soft information ex_decoder/decoder.py:292-316 derives from
+// aligned reads): reads per bit c ~ Poisson(mean) by inversion against the integer thresholds thr[k] =
+// (uint64)(CDF(k) * 2^53) (kVoteMaxReads entries, computed on the host), every read wrong with probability p_err,
+// k = (c - 2 * wrong) for a 0 bit and its negative for a 1 bit (count0 - count1). Integer arithmetic only, so the host
+// twin (oracle/bp_oracle.c:orc_synth_vote) is exact.
+constexpr int kVoteMaxReads = 64;
+__global__ void __launch_bounds__(256)
+synth_vote_kernel(const uint32_t *__restrict__ cw_bits, int n_cw, uint64_t seed, long long frame0, long long F, int N,
+                  int words_per_frame, const uint64_t *__restrict__ thr, uint64_t thr_err, int8_t *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * N) return;
+    const long long fl = t / N;
+    const int j = (int)(t - fl * N);
+    const uint64_t f = (uint64_t)(frame0 + fl);
+    const uint32_t bit = cw_bits ? (cw_bits[(size_t)(f % (uint64_t)n_cw) * words_per_frame + (j >> 5)] >> (j & 31)) & 1u : 0u;
+    const uint64_t u = rng_u64(seed, f, (uint64_t)j, 2) >> 11;
+    int c = 0;
+    while (c < kVoteMaxReads - 1 && u >= __ldg(thr + c)) c++;
+    int wrong = 0;
+    for (int r = 0; r < c; r++) wrong += (rng_u64(seed, f, (uint64_t)j, 3 + (uint64_t)r) >> 11) < thr_err;
+    const int k = c - 2 * wrong;
+    out[t] = (int8_t)(bit ? -k : k);
 }
 
 // ------------------------------------------------------------------------------------------------

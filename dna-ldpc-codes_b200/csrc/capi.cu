@@ -11,6 +11,7 @@
 #include "../../include/dnaldpc.h"
 #include "../host/code.h"
 #include "engine.h"
+#include "sources.h"
 
 using namespace dnaldpc;
 
@@ -138,16 +139,6 @@ int dnaldpc_decoder_create(const dnaldpc_code *c, const dnaldpc_config *cfg, dna
 
 void dnaldpc_decoder_destroy(dnaldpc_decoder *d) { delete d; }
 
-static size_t packed_stride(int kind, int N) {
-    switch (kind) {
-        case DNALDPC_IN_LR_F64: case DNALDPC_IN_LLR_F64: case DNALDPC_IN_AWGN_F64: return (size_t)N * 8;
-        case DNALDPC_IN_AWGN_F32: return (size_t)N * 4;
-        case DNALDPC_IN_BSC_BITS: return (size_t)((N + 31) / 32) * 4;
-        case DNALDPC_IN_VOTE_I8: return (size_t)N;
-    }
-    return 0;
-}
-
 static int check_input(const dnaldpc_input *in, int N) {
     if (!in) return set_err(DNALDPC_ERR_ARG, "null input descriptor");
     if (packed_stride(in->kind, N) == 0) return set_err(DNALDPC_ERR_ARG, "unknown input kind");
@@ -165,42 +156,10 @@ int dnaldpc_decode_batch(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F,
     int rc = check_input(in, d->c.N);
     if (rc) return rc;
     if (F < 0 || max_iter < 0) return set_err(DNALDPC_ERR_ARG, "negative frame count or max_iter");
-    const int nd = (int)d->eng.size();
-    const int M = d->c.M, N = d->c.N;
-    const size_t stride = in->frame_stride ? in->frame_stride : packed_stride(in->kind, N);
-    const size_t wpf = (size_t)(N + 31) / 32;
-    // contiguous block of ceil(F/nd) frames per device, results land in frame order
-    const int64_t per = (F + nd - 1) / nd;
-    std::vector<int> rcs(nd, DNALDPC_OK);
-    auto work = [&](int k) {
-        const int64_t f0 = std::min<int64_t>(F, per * k), f1 = std::min<int64_t>(F, f0 + per);
-        dnaldpc_input w = *in;
-        w.frame_stride = stride;
-        w.data = (const char *)in->data + (size_t)f0 * stride;
-        dnaldpc_output o = *out;
-        if (o.bits) o.bits += (size_t)f0 * wpf;
-        if (o.dblk) o.dblk += (size_t)f0 * N;
-        if (o.iters) o.iters += f0;
-        if (o.is_codeword) o.is_codeword += f0;
-        if (o.posterior) o.posterior += (size_t)f0 * N;
-        if (o.pchk) o.pchk += (size_t)f0 * M;
-        rcs[k] = d->eng[k]->decode_host(w, f1 - f0, max_iter, o);
-    };
-    if (nd == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int k = 0; k < nd; k++) th.emplace_back(work, k);
-        for (auto &t : th) t.join();
-    }
-    d->stats = dnaldpc_stats{};
-    for (int k = 0; k < nd; k++) {
-        if (rcs[k]) return set_err(rcs[k], d->eng[k]->error());
-        const dnaldpc_stats &s = d->eng[k]->stats;
-        d->stats.frames += s.frames; d->stats.frame_iters += s.frame_iters; d->stats.kernel_launches += s.kernel_launches;
-        d->stats.waves += s.waves; d->stats.row_ms += s.row_ms; d->stats.col_ms += s.col_ms;
-        d->stats.compactions += s.compactions;
-    }
-    return DNALDPC_OK;
+    if (F > 0 && !in->data) return set_err(DNALDPC_ERR_ARG, "null input buffer");
+    std::string err;
+    rc = decode_host_batch(d->eng, *in, F, max_iter, *out, d->stats, err);
+    return rc ? set_err(rc, err) : DNALDPC_OK;
 }
 
 int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter,
@@ -208,11 +167,12 @@ int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int
     if (!d || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
     int rc = check_input(in, d->c.N);
     if (rc) return rc;
+    if (F < 0 || max_iter < 0) return set_err(DNALDPC_ERR_ARG, "negative frame count or max_iter");
+    if (F > 0 && !in->data) return set_err(DNALDPC_ERR_ARG, "null input buffer");
     if (in->flags & DNALDPC_FLAG_HOST_EXP) return set_err(DNALDPC_ERR_ARG, "HOST_EXP needs host buffers");
-    rc = d->eng[0]->decode_device(*in, F, max_iter, *out, (cudaStream_t)stream);
-    if (rc) return set_err(rc, d->eng[0]->error());
-    d->stats = d->eng[0]->stats;
-    return DNALDPC_OK;
+    std::string err;
+    rc = decode_device_batch(d->eng, *in, F, max_iter, *out, (cudaStream_t)stream, d->stats, err);
+    return rc ? set_err(rc, err) : DNALDPC_OK;
 }
 
 int dnaldpc_decode_window(dnaldpc_decoder *d, const dnaldpc_window *win, const double *lratio, int64_t F, int max_iter,
@@ -244,17 +204,16 @@ int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_ite
     return DNALDPC_OK;
 }
 
-int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
-                           int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds) {
-    if (!d || !llr || !out || !scales || n_scales <= 0 || F < 0) return set_err(DNALDPC_ERR_ARG, "bad argument");
+// The sweep with libm exp on the host (bit-exact with the reference's exe): the failed frames of a round are gathered
+// on the host, exponentiated there and decoded as a fresh host batch.
+static int sweep_host_exp(dnaldpc_decoder *d, const dnaldpc_input &in0, int64_t F, int max_iter, const double *params,
+                          int n_params, const dnaldpc_output *out, int32_t *rounds) {
     const int M = d->c.M, N = d->c.N;
     const size_t wpf = (size_t)(N + 31) / 32;
+    const size_t stride = in0.frame_stride ? in0.frame_stride : (size_t)N * 8;
     std::vector<uint8_t> ok((size_t)F, 0);
-    dnaldpc_input in{};
-    in.kind = DNALDPC_IN_LLR_F64;
-    in.flags = flags & (DNALDPC_FLAG_HOST_EXP | DNALDPC_FLAG_FIXED_ITERS | DNALDPC_FLAG_MINSUM);
-    in.data = llr;
-    in.param = scales[0];
+    dnaldpc_input in = in0;
+    in.param = params[0];
     dnaldpc_output o = *out;
     o.is_codeword = ok.data();
     int rc = dnaldpc_decode_batch(d, &in, F, max_iter, &o);  // round 0: every frame
@@ -262,20 +221,21 @@ int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int
     if (rounds) for (int64_t f = 0; f < F; f++) rounds[f] = 0;
     dnaldpc_stats total = d->stats;
     std::vector<int64_t> failed;
-    for (int r = 1; r < n_scales; r++) {
+    for (int r = 1; r < n_params; r++) {
         failed.clear();
         for (int64_t f = 0; f < F; f++) if (!ok[(size_t)f]) failed.push_back(f);
         if (failed.empty()) break;
         const size_t K = failed.size();
         std::vector<double> sub(K * (size_t)N);
-        for (size_t k = 0; k < K; k++) memcpy(&sub[k * (size_t)N], llr + (size_t)failed[k] * N, (size_t)N * sizeof(double));
+        for (size_t k = 0; k < K; k++) memcpy(&sub[k * (size_t)N], (const char *)in0.data + (size_t)failed[k] * stride, (size_t)N * sizeof(double));
         std::vector<uint32_t> t_bits(out->bits ? K * wpf : 0);
         std::vector<uint8_t> t_dblk(out->dblk ? K * (size_t)N : 0), t_ok(K), t_pchk(out->pchk ? K * (size_t)M : 0);
         std::vector<int32_t> t_it(K);
         std::vector<double> t_post(out->posterior ? K * (size_t)N : 0);
         dnaldpc_input in2 = in;
         in2.data = sub.data();
-        in2.param = scales[r];
+        in2.frame_stride = 0;
+        in2.param = params[r];
         dnaldpc_output o2{};
         o2.bits = out->bits ? t_bits.data() : nullptr;
         o2.dblk = out->dblk ? t_dblk.data() : nullptr;
@@ -297,10 +257,40 @@ int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int
         }
         total.frames += d->stats.frames; total.frame_iters += d->stats.frame_iters;
         total.kernel_launches += d->stats.kernel_launches; total.waves += d->stats.waves;
+        total.compactions += d->stats.compactions;
     }
     if (out->is_codeword) memcpy(out->is_codeword, ok.data(), (size_t)F);
     d->stats = total;
     return DNALDPC_OK;
+}
+
+int dnaldpc_redecode_sweep_ex(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter, const double *params,
+                              int n_params, const dnaldpc_output *out, int32_t *rounds) {
+    if (!d || !in || !out || !params || n_params <= 0 || F < 0 || max_iter < 0) return set_err(DNALDPC_ERR_ARG, "bad argument");
+    if (F > 0 && !in->data) return set_err(DNALDPC_ERR_ARG, "null input buffer");
+    if (in->kind == DNALDPC_IN_LR_F64) return set_err(DNALDPC_ERR_ARG, "a sweep needs a parameter to vary: LR_F64 inputs have none");
+    if (in->kind == DNALDPC_IN_VOTE_I8 && in->table) return set_err(DNALDPC_ERR_ARG, "a vote-count sweep builds its tables from params[]: table must be NULL");
+    for (int r = 0; r < n_params; r++) {  // every round's parameter has to be valid for the kind
+        dnaldpc_input t = *in;
+        t.param = params[r];
+        const int rc = check_input(&t, d->c.N);
+        if (rc) return rc;
+    }
+    const bool host_exp = in->kind == DNALDPC_IN_LLR_F64 && (in->flags & DNALDPC_FLAG_HOST_EXP) && !(in->flags & DNALDPC_FLAG_MINSUM);
+    if (host_exp) return sweep_host_exp(d, *in, F, max_iter, params, n_params, out, rounds);
+    std::string err;
+    const int rc = redecode_sweep_batch(d->eng, *in, F, max_iter, params, n_params, *out, rounds, d->stats, err);
+    return rc ? set_err(rc, err) : DNALDPC_OK;
+}
+
+int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
+                           int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds) {
+    if (!d || !llr || !out || !scales || n_scales <= 0 || F < 0) return set_err(DNALDPC_ERR_ARG, "bad argument");
+    dnaldpc_input in{};
+    in.kind = DNALDPC_IN_LLR_F64;
+    in.flags = flags & (DNALDPC_FLAG_HOST_EXP | DNALDPC_FLAG_FIXED_ITERS | DNALDPC_FLAG_MINSUM);
+    in.data = llr;
+    return dnaldpc_redecode_sweep_ex(d, &in, F, max_iter, scales, n_scales, out, rounds);
 }
 
 double dnaldpc_std_dev(double ebno_db, double rate) {  // channel.cpp:9-16
@@ -326,6 +316,20 @@ int dnaldpc_synth_bsc_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_
                              int64_t F, double eps, uint32_t *out_bits, void *stream) {
     if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
     int rc = d->eng[0]->synth_bsc(cw_bits, n_cw, seed, frame0, F, eps, out_bits, (cudaStream_t)stream);
+    return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
+}
+
+int dnaldpc_synth_awgn_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
+                              int64_t F, double sigma, float *out_y, void *stream) {
+    if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
+    int rc = d->eng[0]->synth_awgn(cw_bits, n_cw, seed, frame0, F, sigma, out_y, (cudaStream_t)stream);
+    return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
+}
+
+int dnaldpc_synth_vote_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
+                              int64_t F, double mean_reads, double read_err, int8_t *out_k, void *stream) {
+    if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
+    int rc = d->eng[0]->synth_vote(cw_bits, n_cw, seed, frame0, F, mean_reads, read_err, out_k, (cudaStream_t)stream);
     return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
 }
 

@@ -63,27 +63,33 @@ Engine::Engine(const Code &code, int device, int precision, int wave_frames)
     up(&d_col_ptr_, code.col_ptr);
     up(&d_col_edge_, code.col_edge);
     chk(cudaMalloc((void **)&d_table_, 256 * sizeof(double)), "cudaMalloc(table)");
-    chk(cudaMalloc((void **)&d_next_, sizeof(unsigned long long)), "cudaMalloc(next)");
-    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * 3 * sizeof(unsigned)), "cudaMalloc(counters)");
-    chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * 3 * sizeof(unsigned)), "cudaMallocHost(counters)");
+    chk(cudaMalloc((void **)&d_next_, 3 * sizeof(unsigned long long)), "cudaMalloc(next)");
+    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * kCounterWords * sizeof(unsigned)), "cudaMalloc(counters)");
+    chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * kCounterWords * sizeof(unsigned)), "cudaMallocHost(counters)");
+    chk(cudaEventCreateWithFlags(&ready_ev_, cudaEventDisableTiming), "cudaEventCreate");
     chk(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_), "cudaDeviceGetAttribute");
     for (auto &e : ev_) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     for (auto &e : prof_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
     for (auto &e : trace_ev_) chk(cudaEventCreate(&e), "cudaEventCreate");
     chk(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto &s : io_stream_) chk(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
 Engine::~Engine() {
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
-                    d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_};
+                    d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_,
+                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1]};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
+    if (h_bounce_) cudaFreeHost(h_bounce_);
+    if (ready_ev_) cudaEventDestroy(ready_ev_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
     for (auto &e : trace_ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
+    for (auto &s : io_stream_) if (s) cudaStreamDestroy(s);
 }
 
 int Engine::ensure_slots(int G, bool want_post) {
@@ -125,6 +131,10 @@ void Engine::fill_sched(SchedArrays &s) const {
     const size_t S = G * kFG;
     s.slot_frame = d_slot_; s.slot_iter = d_slot_ + S; s.harv_frame = d_slot_ + 2 * S; s.harv_iter = d_slot_ + 3 * S;
     s.next_frame = d_next_;
+    s.avail = d_next_ + 1;
+    s.iter_sum = d_next_ + 2;
+    s.in_row = d_rows_;
+    s.out_row = d_rows_ + cap_rows_;
 }
 
 // ---- kernel dispatch -----------------------------------------------------------------------------
@@ -193,18 +203,20 @@ template <typename T> int Engine::launch_col(int g0, int G, bool want_post, cuda
 
 // check() + loop control for the slots under consideration (syndrome_update_*_kernel)
 int Engine::launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int consider_new, int fixed, unsigned *counter,
-                            unsigned *finished, unsigned *rearm, int clear_fresh, int64_t F, cudaStream_t st) {
+                            unsigned *finished, unsigned *rearm, int clear_fresh, cudaStream_t st) {
     SchedArrays s;
     fill_sched(s);
     SynArgs a;
     a.iters_out = out.iters; a.ok_out = out.is_codeword;
     a.M = M_; a.N = N_; a.g0 = 0; a.max_iter = max_iter; a.consider_new = consider_new; a.fixed_iters = fixed;
-    a.counter = counter; a.finished = finished; a.counters_to_zero = rearm; a.clear_fresh = clear_fresh; a.F = (long long)F;
+    a.counter = counter; a.finished = finished; a.counters_to_zero = rearm; a.clear_fresh = clear_fresh;
     const size_t smem = (size_t)N_ * sizeof(uint32_t);
     static const bool no_smem = getenv("DNALDPC_SYN_GATHER") != nullptr;  // A/B switch: global-gather variant
-    if (!no_smem && smem <= 96 * 1024 && N_ % 4 == 0) {  // the group's decision words staged in shared memory
+    if (!no_smem && smem <= (size_t)kSynSmemGate && N_ % 4 == 0) {  // the group's decision words staged in shared memory
         if (!syn_attr_set_) {
-            CK(cudaFuncSetAttribute(syndrome_update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // The attribute is global per (function, device): always raise it to the fixed gate value so that decoders
+            // for different codes on one GPU cannot lower each other's limit.
+            CK(cudaFuncSetAttribute(syndrome_update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemGate));
             syn_attr_set_ = true;
         }
         syndrome_update_smem_kernel<<<dim3(kSynSmemSplit, (unsigned)G), kSynSmemThreads, smem, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
@@ -257,19 +269,49 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
     return DNALDPC_OK;
 }
 
-// ---- one batch: every frame of [0, F) flows through the slots ---------------------------------------
+// ---- one batch: every frame the source publishes flows through the slots ------------------------------
+
+int Engine::ensure_rows(int64_t frames) {
+    if (frames > cap_rows_) {
+        if (d_rows_) cudaFree(d_rows_);
+        d_rows_ = nullptr; cap_rows_ = 0;
+        CK(cudaMalloc((void **)&d_rows_, (size_t)frames * 2 * sizeof(int32_t)));
+        cap_rows_ = frames;
+    }
+    return DNALDPC_OK;
+}
+
+int Engine::set_device() {
+    CK(cudaSetDevice(device_));
+    return DNALDPC_OK;
+}
+
+int Engine::publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream) {
+    if (n <= 0) return DNALDPC_OK;
+    const int64_t q0 = published_.load(std::memory_order_relaxed);
+    if (q0 + n > cap_rows_) return fail("frame queue overflow (more frames published than the session announced)", DNALDPC_ERR_ARG);
+    publish_kernel<<<1, 1024, 0, stream>>>(d_rows_, d_rows_ + cap_rows_, (long long)q0, n, list_in, row0_in, row0_out, d_next_ + 1);
+    CK(cudaGetLastError());
+    published_.store(q0 + n, std::memory_order_release);
+    return DNALDPC_OK;
+}
 
 template <typename T>
-int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out_user, cudaStream_t st) {
-    if (F == 0) return DNALDPC_OK;
-    if (F > 0x7fffffffLL) return fail("more than 2^31-1 frames in one call", DNALDPC_ERR_ARG);
-    const int G = (int)std::min<int64_t>((F + 31) / 32, wave_frames_ / 32);
-    const bool want_post = out_user.posterior != nullptr;
+int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
+    const dnaldpc_input &in = ss.in;
+    const int64_t Fmax = ss.max_frames;
+    if (Fmax <= 0) return DNALDPC_OK;
+    if (Fmax > 0x7fffffffLL) return fail("more than 2^31-1 frames in one call", DNALDPC_ERR_ARG);
+    const int G = (int)std::min<int64_t>((Fmax + 31) / 32, wave_frames_ / 32);
+    const long long S = (long long)G * kFG;
+    const bool want_post = ss.out.posterior != nullptr;
     int rc = ensure_slots(G, want_post);
     if (rc) return rc;
-    dnaldpc_output out = out_user;
-    if (!out.iters || !out.is_codeword) {
-        rc = ensure_frame_scratch(F);
+    rc = ensure_rows(Fmax);
+    if (rc) return rc;
+    dnaldpc_output out = ss.out;
+    if (!out.iters || !out.is_codeword) {  // indexed by output row: the caller's rows are below max_frames here
+        rc = ensure_frame_scratch(Fmax);
         if (rc) return rc;
         if (!out.iters) out.iters = d_iters_;
         if (!out.is_codeword) out.is_codeword = d_ok_;
@@ -278,90 +320,112 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
     if (in.kind == DNALDPC_IN_BSC_BITS || in.kind == DNALDPC_IN_VOTE_I8) {
         double tab[256];
         int cnt = 256;
+        bool user_table = false;
         if (in.kind == DNALDPC_IN_BSC_BITS) {
             dnaldpc_bsc_table(in.param, tab);
             cnt = 2;
             if (minsum_) { tab[0] = std::log(tab[0]); tab[1] = std::log(tab[1]); }  // received_LLR = log(received_LR), channel.cpp:78,83
-        } else if (in.table) memcpy(tab, in.table, sizeof(tab));  // caller's table: ratios for BP, LLRs for min-sum
+        } else if (in.table) user_table = true;  // caller's table (HOST or DEVICE pointer): ratios for BP, LLRs for min-sum
         else if (minsum_) {
             const double L = std::log((1 - in.param) / in.param);
             for (int k = -128; k < 128; k++) tab[k + 128] = k * L;                   // decoder.py:314
         } else dnaldpc_vote_table(in.param, tab);
-        // pageable source: copied to a driver staging buffer before the call returns
-        CK(cudaMemcpyAsync(d_table_, tab, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        // pageable source: copied to a driver staging buffer before the call returns. A caller's table may live on
+        // either side (cudaMemcpyDefault resolves it through unified addressing).
+        if (user_table) CK(cudaMemcpyAsync(d_table_, in.table, 256 * sizeof(double), cudaMemcpyDefault, st));
+        else CK(cudaMemcpyAsync(d_table_, tab, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     SchedArrays s;
     fill_sched(s);
-    init_sched_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(s, G);
+    published_.store(0, std::memory_order_release);
+    init_sched_kernel<<<(G * kFG + 255) / 256, 256, 0, st>>>(s, G, d_counters_, kRing);
     stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(d_counters_, 0, (size_t)kRing * 3 * sizeof(unsigned), st));
+    // the queue is empty and *avail == 0 from here on in stream order; producers on other streams wait for this point
+    CK(cudaEventRecord(ready_ev_, st));
     steady_ = false;
     traced_ = 0;
 
     // One tick = admit/harvest/check (twice) + one check-node pass + one bit-node pass over all slots.
     // (Measured alternative, removed: two halves of the groups ticking on two streams so that one half's kernel tail is
     // filled by the other's next kernel: +0.4 % with the register-resident check kernel, -3 % with the smem-staged one.)
-    unsigned last_busy = 0, last_admitted = 1, last_finished = 1;  // what the host knows (kLag ticks old)
-    // Drain tail: once every frame has been admitted (sum of the polled `admitted` counters == F) finished slots stay
-    // empty and the stragglers thin out over all groups; whenever fewer than kCompactFrac of the slots of the packed
-    // region are still busy they are compacted into the lowest groups (compact_*_kernel) and the check / bit passes
-    // shrink to those groups.
+    unsigned last_inuse = 0, last_admitted = 1, last_finished = 1;  // what the host knows (kLag ticks old)
+    // Drain tail: once every frame has been admitted (the source is final and the polled `admitted` counters add up to
+    // what was published) finished slots stay empty and the stragglers thin out over all groups; whenever at most
+    // kCompactNum / kCompactDen (15/16, about 93 %) of the slots of the packed region are still busy they are compacted
+    // into the lowest groups (compact_*_kernel) and the check / bit passes shrink to those groups.
     const bool no_compact = getenv("DNALDPC_NO_COMPACT") != nullptr;  // A/B switch, read per batch
-    // threshold in per cent of the packed region (default kCompactNum / kCompactDen = 50); tests raise it to make the
-    // batch compact at almost every tick
+    // threshold in per cent of the packed region (default 100 * kCompactNum / kCompactDen = 93); tests set it to
+    // exercise other compaction schedules
     const long long compact_pct = getenv("DNALDPC_COMPACT_PCT") ? std::max(1, std::min(99, atoi(getenv("DNALDPC_COMPACT_PCT")))) : 100LL * kCompactNum / kCompactDen;
-    long long admitted_total = 0;
-    int G_rc = G;                             // groups the check / bit passes are launched over
-    long long packed_cap = (long long)G * kFG;  // slots of the region the busy slots were last packed into
+    long long admitted_total = 0, low_water = 0;
+    bool final = false;
+    bool admit_ring[kRing] = {};
+    int G_rc = G;                  // groups the check / bit passes are launched over
+    long long packed_cap = S;      // slots of the region the busy slots were last packed into
+    const int fixed = (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0;
     for (long long tick = 0;; tick++) {
-        // ring entry of this tick: [0] busy slots + pending frames, [1] frames admitted, [2] frames finished
-        unsigned *cnt = d_counters_ + 3 * (tick % kRing);
-        unsigned *rearm = d_counters_ + 3 * ((tick + kRing / 2) % kRing);
-        const int fixed = (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0;
+        rc = src.pump(*this, admitted_total, low_water, &final);
+        if (rc) return rc;
+        const long long pub = published();
+        // ring entry of this tick: [0] slots in use, [1] frames admitted, [2] frames finished, [3] low-water q
+        unsigned *cnt = d_counters_ + kCounterWords * (tick % kRing);
+        unsigned *rearm = d_counters_ + kCounterWords * ((tick + kRing / 2) % kRing);
         // Admission (assign + harvest/setup, twice) is only launched when the host has reason to expect work for it:
-        // start-up, a frame finished or was admitted kLag ticks ago, or slots are idle. In the steady state of long
-        // frames a tick is just syndrome -> check pass -> bit pass; a finish is then picked up at most kLag ticks late.
-        const bool admit = tick < 2 + kLag || last_finished > 0 || last_admitted > 0 || last_busy < (unsigned)G * kFG;
+        // start-up, a frame finished or was admitted kLag ticks ago, or slots are idle while frames wait. In the steady
+        // state of long frames a tick is just syndrome -> check pass -> bit pass; a finish is then picked up at most
+        // kLag ticks late.
+        const bool admit = tick < 2 + kLag || last_finished > 0 || last_admitted > 0 || (last_inuse < (unsigned)S && pub > admitted_total);
+        admit_ring[tick % kRing] = admit;
         if (admit) {
             // Two admission rounds: slots that finish in round 1 (incl. frames that need no iteration at all) are
             // harvested and refilled at once, so a slot idles at most in the rare case of two finishes in a row.
             for (int round = 1; round <= 2; round++) {
-                assign_kernel<<<(G + 7) / 8, 256, 0, st>>>(s, (long long)F, 0, G, round == 1, cnt + 1);
+                assign_kernel<<<(G + 7) / 8, 256, 0, st>>>(s, 0, G, round == 1, cnt + 1, cnt + 3);
                 stats.kernel_launches++;
                 rc = launch_harvest_setup<T>(in, out, 0, G, st);
                 if (rc) return rc;
-                rc = launch_syndrome(out, G, max_iter, round == 2, fixed, round == 2 ? cnt : nullptr, cnt + 2,
-                                     round == 1 ? rearm : nullptr, 0, F, st);
+                rc = launch_syndrome(out, G, ss.max_iter, round == 2, fixed, round == 2 ? cnt : nullptr, cnt + 2,
+                                     round == 1 ? rearm : nullptr, 0, st);
                 if (rc) return rc;
             }
         } else {
-            rc = launch_syndrome(out, G, max_iter, 0, fixed, cnt, cnt + 2, rearm, 1, F, st);
+            rc = launch_syndrome(out, G, ss.max_iter, 0, fixed, cnt, cnt + 2, rearm, 1, st);
             if (rc) return rc;
         }
-        CK(cudaMemcpyAsync(h_counters_ + 3 * (tick % kRing), cnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_counters_ + kCounterWords * (tick % kRing), cnt, kCounterWords * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev_[tick % kRing], st));
         if (tick >= kLag) {  // lagged poll: the host runs at most kLag ticks ahead of the device
-            CK(cudaEventSynchronize(ev_[(tick - kLag) % kRing]));
-            const unsigned *hc = h_counters_ + 3 * ((tick - kLag) % kRing);
-            last_busy = hc[0]; last_admitted = hc[1]; last_finished = hc[2];
-            if (last_busy == 0) break;  // drained: nothing active, finished-unharvested or pending
-            // steady state = every slot busy and nobody being admitted (e.g. long-running frames): the smem-staged
-            // check kernel wins there (+2.5 %); with refills or idle slots the register kernel is faster
-            steady_ = last_admitted == 0 && last_busy >= (unsigned)G * kFG;
+            const long long t = tick - kLag;
+            CK(cudaEventSynchronize(ev_[t % kRing]));
+            const unsigned *hc = h_counters_ + kCounterWords * (t % kRing);
+            last_inuse = hc[0]; last_admitted = hc[1]; last_finished = hc[2];
             admitted_total += last_admitted;
-            if (!no_compact && !profiling && admitted_total >= F && packed_cap >= 2 * kFG &&
-                (long long)last_busy * 100 <= packed_cap * compact_pct) {
-                // `last_busy` is kLag ticks old and can only have shrunk since: it bounds the moves and the packed size
+            // every q below the smallest one that was still in a slot after tick t's admission has been harvested by
+            // tick t's harvest kernels, which have completed (the event above); without admission nothing was harvested
+            if (admit_ring[t % kRing]) low_water = std::min<long long>(hc[3] == 0xffffffffu ? admitted_total : (long long)hc[3], admitted_total);
+            if (final && admitted_total == published() && last_inuse == 0) break;  // drained: nothing active, unharvested or pending
+            // steady state = every slot busy and nobody being admitted (e.g. long-running frames)
+            steady_ = last_admitted == 0 && last_inuse >= (unsigned)S;
+            if (!final && last_inuse == 0 && admitted_total == published()) {
+                // idle engine, starved source: do not spin empty ticks
+                src.wait_for_frames();
+                last_admitted = 1;  // look for frames in the next tick
+                continue;
+            }
+            if (!no_compact && !profiling && final && admitted_total == published() && packed_cap >= 2 * kFG &&
+                (long long)last_inuse * 100 <= packed_cap * compact_pct) {
+                // `last_inuse` is kLag ticks old and can only have shrunk since: it bounds the moves and the packed size
                 int32_t *mv_src = d_mv_, *mv_dst = d_mv_ + (size_t)cap_groups_ * kFG, *mv_cnt = d_mv_ + (size_t)cap_groups_ * kFG * 2;
                 compact_plan_kernel<<<1, 32, 0, st>>>(s, G, mv_src, mv_dst, mv_cnt);
                 dim3 mgrid((unsigned)((E_ + N_ + kMoveThreads * kMoveUnroll - 1) / (kMoveThreads * kMoveUnroll)),
-                           (unsigned)std::min<unsigned>(last_busy, 2048u));
+                           (unsigned)std::min<unsigned>(std::max(last_inuse, 1u), 2048u));
                 compact_move_kernel<T><<<mgrid, kMoveThreads, 0, st>>>((T *)d_msg_, (T *)d_lratio_, mv_src, mv_dst, mv_cnt, N_, E_);
                 stats.kernel_launches += 2;
                 stats.compactions++;
                 CK(cudaGetLastError());
-                G_rc = (int)std::min<long long>(G, ((long long)last_busy + kFG - 1) / kFG);
+                G_rc = (int)std::min<long long>(G, ((long long)last_inuse + kFG - 1) / kFG);
+                G_rc = std::max(G_rc, 1);
                 packed_cap = (long long)G_rc * kFG;
             }
         }
@@ -386,7 +450,15 @@ int Engine::run(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_
             stats.waves++;  // profiled ticks
         }
     }
-    return DNALDPC_OK;
+    // the loop ended on a host-synchronised event that follows the last harvest: the iteration sum is final
+    unsigned long long it_sum = 0;
+    CK(cudaMemcpyAsync(&it_sum, d_next_ + 2, sizeof(it_sum), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    stats.frame_iters = (int64_t)it_sum;
+    stats.frames = admitted_total;
+    low_water = admitted_total;
+    rc = src.pump(*this, admitted_total, low_water, &final);  // lets the source retire the last outputs
+    return rc;
 }
 
 // In-pipeline timing of ticks 8..8+n (events recorded without any synchronisation; call after the stream has drained):
@@ -408,107 +480,34 @@ int Engine::trace_result(double *row_ms, double *col_ms, double *sched_ms) {
     return traced_;
 }
 
-int Engine::decode_device(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out, cudaStream_t stream) {
+int Engine::run_session(const Session &ss, FrameSource &src, cudaStream_t stream) {
     if (!err_.empty() && d_row_ptr_ == nullptr) return DNALDPC_ERR_CUDA;
     err_.clear();
-    if (F < 0 || max_iter < 0 || (F > 0 && in.data == nullptr)) return fail("bad argument", DNALDPC_ERR_ARG);
+    if (ss.max_frames < 0 || ss.max_iter < 0) return fail("bad argument", DNALDPC_ERR_ARG);
     CK(cudaSetDevice(device_));
     stats = dnaldpc_stats{};
-    stats.frames = F;
-    dnaldpc_input w = in;
-    w.frame_stride = in.frame_stride ? in.frame_stride : in_elem_stride(in.kind, N_);
-    if (w.frame_stride == 0) return fail("unknown input kind", DNALDPC_ERR_ARG);
-    return precision_ == DNALDPC_PREC_F32 ? run<float>(w, F, max_iter, out, stream) : run<double>(w, F, max_iter, out, stream);
+    cudaStream_t st = stream ? stream : own_stream_;
+    return precision_ == DNALDPC_PREC_F32 ? run<float>(ss, src, st) : run<double>(ss, src, st);
 }
 
 void *Engine::stage(void **buf, size_t *cap, size_t need) {
     if (need > *cap) {
         if (*buf) cudaFree(*buf);
         *buf = nullptr; *cap = 0;
-        if (cudaMalloc(buf, need) != cudaSuccess) return nullptr;
+        if (cudaMalloc(buf, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         *cap = need;
     }
     return *buf;
 }
 
-int Engine::decode_host(const dnaldpc_input &in, int64_t F, int max_iter, const dnaldpc_output &out) {
-    if (!err_.empty() && d_row_ptr_ == nullptr) return DNALDPC_ERR_CUDA;
-    err_.clear();
-    if (F < 0 || max_iter < 0 || (F > 0 && in.data == nullptr)) return fail("bad argument", DNALDPC_ERR_ARG);
-    CK(cudaSetDevice(device_));
-    cudaStream_t st = own_stream_;
-    dnaldpc_stats acc{};
-    acc.frames = F;
-    const size_t stride = in.frame_stride ? in.frame_stride : in_elem_stride(in.kind, N_);
-    const size_t packed = in_elem_stride(in.kind, N_);
-    if (packed == 0) return fail("unknown input kind", DNALDPC_ERR_ARG);
-    const size_t wpf = (size_t)(N_ + 31) / 32;
-    const bool host_exp = in.kind == DNALDPC_IN_LLR_F64 && (in.flags & DNALDPC_FLAG_HOST_EXP) && !(in.flags & DNALDPC_FLAG_MINSUM);
-    // Host batches are staged to the device in chunks; inside a chunk frames flow continuously through the slots.
-    const int64_t budget = (int64_t)3 << 30;  // ~3 GB of staged input + outputs per chunk
-    const size_t per_frame = packed + (out.bits ? wpf * 4 : 0) + (out.dblk ? (size_t)N_ : 0) + (out.posterior ? (size_t)N_ * 8 : 0) +
-                             (out.pchk ? (size_t)M_ : 0) + 8;
-    int64_t chunk = std::max<int64_t>((int64_t)wave_frames_ * 4, budget / (int64_t)per_frame);
-    chunk = std::min<int64_t>(chunk, 1 << 20);
-    for (int64_t f0 = 0; f0 < F; f0 += chunk) {
-        const int64_t nf = std::min<int64_t>(chunk, F - f0);
-        if (!stage(&s_in_, &c_in_, (size_t)nf * packed)) return fail("out of device memory (input staging)", DNALDPC_ERR_NOMEM);
-        const char *src = (const char *)in.data + (size_t)f0 * stride;
-        dnaldpc_input w = in;
-        if (host_exp) {  // LR = exp(LLR) with the host libm, like LDPC_Encode (DNA_main.cpp:1344)
-            h_exp_.resize((size_t)nf * N_);
-            const double sc = in.param == 0.0 ? 1.0 : in.param;
-            auto exp_rows = [&](int64_t fa, int64_t fb) {
-                for (int64_t f = fa; f < fb; f++) {
-                    const double *row = (const double *)(src + (size_t)f * stride);
-                    for (int j = 0; j < N_; j++) h_exp_[(size_t)f * N_ + j] = std::exp(sc == 1.0 ? row[j] : sc * row[j]);
-                }
-            };
-            // libm exp is ~20 ns per value: a large batch is split over the host cores (same libm, same results)
-            const int nthr = (int)std::min<int64_t>({(int64_t)std::max(1u, std::thread::hardware_concurrency()), (int64_t)32, nf / 8 + 1});
-            if (nthr <= 1) exp_rows(0, nf);
-            else {
-                std::vector<std::thread> th;
-                for (int t = 0; t < nthr; t++) th.emplace_back(exp_rows, nf * t / nthr, nf * (t + 1) / nthr);
-                for (auto &t : th) t.join();
-            }
-            CK(cudaMemcpyAsync(s_in_, h_exp_.data(), (size_t)nf * packed, cudaMemcpyHostToDevice, st));
-            w.kind = DNALDPC_IN_LR_F64;
-        } else if (stride == packed) {
-            CK(cudaMemcpyAsync(s_in_, src, (size_t)nf * packed, cudaMemcpyHostToDevice, st));
-        } else {
-            CK(cudaMemcpy2DAsync(s_in_, packed, src, stride, packed, (size_t)nf, cudaMemcpyHostToDevice, st));
-        }
-        w.data = s_in_;
-        w.frame_stride = packed;
-        dnaldpc_output o{};
-        if (out.bits && !(o.bits = (uint32_t *)stage(&s_bits_, &c_bits_, (size_t)nf * wpf * 4))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
-        if (out.dblk && !(o.dblk = (uint8_t *)stage(&s_dblk_, &c_dblk_, (size_t)nf * N_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
-        if (out.posterior && !(o.posterior = (double *)stage(&s_post_, &c_post_, (size_t)nf * N_ * 8))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
-        if (out.pchk && !(o.pchk = (uint8_t *)stage(&s_pchk_, &c_pchk_, (size_t)nf * M_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
-        int rc = ensure_frame_scratch(nf);
-        if (rc) return rc;
-        o.iters = d_iters_;
-        o.is_codeword = d_ok_;
-        stats = dnaldpc_stats{};
-        rc = precision_ == DNALDPC_PREC_F32 ? run<float>(w, nf, max_iter, o, st) : run<double>(w, nf, max_iter, o, st);
-        if (rc) return rc;
-        acc.kernel_launches += stats.kernel_launches;
-        acc.waves += stats.waves;
-        acc.row_ms += stats.row_ms;
-        acc.col_ms += stats.col_ms;
-        acc.compactions += stats.compactions;
-        if (out.bits) CK(cudaMemcpyAsync(out.bits + (size_t)f0 * wpf, o.bits, (size_t)nf * wpf * 4, cudaMemcpyDeviceToHost, st));
-        if (out.dblk) CK(cudaMemcpyAsync(out.dblk + (size_t)f0 * N_, o.dblk, (size_t)nf * N_, cudaMemcpyDeviceToHost, st));
-        if (out.posterior) CK(cudaMemcpyAsync(out.posterior + (size_t)f0 * N_, o.posterior, (size_t)nf * N_ * 8, cudaMemcpyDeviceToHost, st));
-        if (out.pchk) CK(cudaMemcpyAsync(out.pchk + (size_t)f0 * M_, o.pchk, (size_t)nf * M_, cudaMemcpyDeviceToHost, st));
-        if (out.iters) CK(cudaMemcpyAsync(out.iters + f0, d_iters_, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-        if (out.is_codeword) CK(cudaMemcpyAsync(out.is_codeword + f0, d_ok_, (size_t)nf, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+void *Engine::pinned(size_t need) {
+    if (need > c_bounce_) {
+        if (h_bounce_) cudaFreeHost(h_bounce_);
+        h_bounce_ = nullptr; c_bounce_ = 0;
+        if (cudaMallocHost(&h_bounce_, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        c_bounce_ = need;
     }
-    stats = acc;
-    if (out.iters) for (int64_t f = 0; f < F; f++) stats.frame_iters += out.iters[f];
-    return DNALDPC_OK;
+    return h_bounce_;
 }
 
 // ---- sliding-window BP for spatially-coupled codes ------------------------------------
@@ -655,6 +654,63 @@ int Engine::synth_bsc(const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t 
     if (total == 0) return DNALDPC_OK;
     const uint64_t thr = (uint64_t)(eps * 9007199254740992.0);
     synth_bsc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cw_bits, n_cw, seed, frame0, F, N_, wpf, thr, out_bits);
+    CK(cudaGetLastError());
+    return DNALDPC_OK;
+}
+
+int Engine::synth_awgn(const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0, int64_t F, double sigma,
+                       float *out_y, cudaStream_t stream) {
+    err_.clear();
+    if (F < 0 || !out_y || (cw_bits && n_cw <= 0) || !(sigma >= 0.0)) return fail("bad argument", DNALDPC_ERR_ARG);
+    CK(cudaSetDevice(device_));
+    const long long total = (long long)F * N_;
+    if (total == 0) return DNALDPC_OK;
+    synth_awgn_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cw_bits, n_cw, seed, frame0, F, N_, (N_ + 31) / 32, sigma, out_y);
+    CK(cudaGetLastError());
+    return DNALDPC_OK;
+}
+
+// thr[k] = (uint64)(P(Poisson(mean) <= k) * 2^53), k = 0 .. kVoteMaxReads-1 (pmf by the recurrence p_k = p_{k-1} * mean / k
+// from p_0 = exp(-mean), summed in ascending k): the host twin oracle/bp_oracle.c:orc_vote_thresholds does the same.
+void vote_thresholds(double mean, uint64_t *thr) {
+    double p = std::exp(-mean), cdf = 0;
+    for (int k = 0; k < kVoteMaxReads; k++) {
+        if (k > 0) p = p * mean / k;
+        cdf += p;
+        thr[k] = (uint64_t)(std::min(cdf, 1.0) * 9007199254740992.0);
+    }
+}
+
+int Engine::synth_vote(const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0, int64_t F, double mean_reads,
+                       double read_err, int8_t *out_k, cudaStream_t stream) {
+    err_.clear();
+    if (F < 0 || !out_k || (cw_bits && n_cw <= 0) || !(mean_reads > 0.0 && mean_reads <= 32.0) || !(read_err >= 0.0 && read_err <= 1.0))
+        return fail("bad argument (mean reads in (0, 32], read error in [0, 1])", DNALDPC_ERR_ARG);
+    CK(cudaSetDevice(device_));
+    const long long total = (long long)F * N_;
+    if (total == 0) return DNALDPC_OK;
+    uint64_t thr[kVoteMaxReads];
+    vote_thresholds(mean_reads, thr);
+    if (!d_synth_thr_) CK(cudaMalloc((void **)&d_synth_thr_, sizeof(thr)));
+    CK(cudaMemcpyAsync(d_synth_thr_, thr, sizeof(thr), cudaMemcpyHostToDevice, stream));  // pageable: staged before the call returns
+    const uint64_t thr_err = (uint64_t)(read_err * 9007199254740992.0);
+    synth_vote_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cw_bits, n_cw, seed, frame0, F, N_, (N_ + 31) / 32, d_synth_thr_, thr_err, out_k);
+    CK(cudaGetLastError());
+    return DNALDPC_OK;
+}
+
+int Engine::ensure_lists(int64_t n) {
+    if (n + 1 > cap_list_) {
+        for (auto &p : d_list_) { if (p) cudaFree(p); p = nullptr; }
+        cap_list_ = 0;
+        for (auto &p : d_list_) CK(cudaMalloc((void **)&p, (size_t)(n + 1) * sizeof(int32_t)));  // [n] rows + the count
+        cap_list_ = n + 1;
+    }
+    return DNALDPC_OK;
+}
+
+int Engine::failed_rows(const uint8_t *ok, const int32_t *prev_list, int n, int32_t *list_out, int32_t *count_dev, cudaStream_t stream) {
+    failed_rows_kernel<<<1, 1024, 0, stream>>>(ok, prev_list, n, list_out, count_dev);
     CK(cudaGetLastError());
     return DNALDPC_OK;
 }

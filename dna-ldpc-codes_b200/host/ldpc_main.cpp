@@ -170,10 +170,10 @@ int main(int argc, char **argv) {
     // CUDA context creation dominates a one-process run (about a second); it runs on its own thread while the input
     // text is parsed. A one-frame run is dominated by it anyway; exposing only the requested GPU to the driver keeps it
     // from initialising every device of an 8-GPU box (the variable is only set when the caller has not set it).
-    {
+    if (getenv("CUDA_VISIBLE_DEVICES") == nullptr) {  // remap only when WE narrowed the view: a caller's own setting keeps its ordinals
         char dev[16];
         snprintf(dev, sizeof(dev), "%d", a.device);
-        if (setenv("CUDA_VISIBLE_DEVICES", dev, 0) == 0 && std::string(getenv("CUDA_VISIBLE_DEVICES")) == dev) a.device = 0;
+        if (setenv("CUDA_VISIBLE_DEVICES", dev, 0) == 0) a.device = 0;
     }
     dnaldpc_config cfg{};
     cfg.n_devices = 1;
@@ -251,7 +251,7 @@ int main(int argc, char **argv) {
 
     // error counting: LDPC_Raw_Error_Check (:1711-1750, sign of the LLR) and LDPC_BIT_Check (:1675-1706)
     const int len = a.bSystematic ? K : N;
-    long long bit_err[3] = {0, 0, 0}, frame_err[3] = {0, 0, 0}, total_iter = 0;
+    long long bit_err[3] = {0, 0, 0}, frame_err[3] = {0, 0, 0}, total_iter = 0, n_converged = 0;
     for (size_t f = 0; f < F; f++) {
         long long raw = 0, dec_err = 0;
         for (int i = 0; i < len; i++) {
@@ -266,6 +266,7 @@ int main(int argc, char **argv) {
         bit_err[1] += dec_err; frame_err[1] += dec_err > 0;
         bit_err[2] += dec_err; frame_err[2] += dec_err > 0;
         total_iter += iters[f];
+        n_converged += okflag[f] != 0;  // zero syndrome (`*bIsCodeword`), whether or not it is the codeword that was sent
     }
     // frame_num > 1 re-reads the same files and repeats the identical decode (DNA_main.cpp:1319-1348): counters scale
     const long long reps = a.list.empty() ? a.frame_num : 1;
@@ -341,7 +342,7 @@ int main(int argc, char **argv) {
         const double ms = std::chrono::duration<double, std::milli>(c1 - c0).count();
         const double init_ms = std::chrono::duration<double, std::milli>(i1 - i0).count();
         fprintf(stderr, "{\"frames\": %zu, \"gpu_init_ms\": %.1f, \"decode_ms\": %.3f, \"total_iterations\": %lld, \"converged\": %lld}\n", F, init_ms, ms,
-                total_iter, (long long)F - frame_err[2] / (reps ? reps : 1));
+                total_iter, n_converged);
     }
     dnaldpc_decoder_destroy(dec);
     dnaldpc_code_free(code);

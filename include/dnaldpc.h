@@ -63,7 +63,7 @@ int dnaldpc_code_check_regular(const dnaldpc_code *c, int *dv, int *regular_dv, 
 
 typedef struct dnaldpc_config {
     int32_t n_devices;      /* 0 = current device only */
-    int32_t devices[16];    /* CUDA ordinals; frames of a host batch are sharded contiguously across them */
+    int32_t devices[16];    /* CUDA ordinals; the frames of a batch are pulled by them in chunks from one shared counter */
     int32_t precision;      /* DNALDPC_PREC_* */
     int32_t wave_frames;    /* frames resident per device at once (rounded up to 32); 0 = default (4096) */
     int32_t flags;          /* reserved, 0 */
@@ -101,7 +101,7 @@ typedef struct dnaldpc_input {
     const void *data;    /* frame-major, frame f at data + f*frame_stride bytes */
     size_t frame_stride; /* 0 = tightly packed for the kind */
     double param;        /* p | sigma | eps, per kind; LLR kinds: scale s, LR = exp(s*LLR) (0 = 1.0) */
-    const double *table; /* VOTE_I8 only: optional LR table[256] indexed by (k+128); NULL = exp(k*L) by libm */
+    const double *table; /* VOTE_I8 only: optional LR table[256] indexed by (k+128), HOST or DEVICE memory; NULL = exp(k*L) by libm */
 } dnaldpc_input;
 
 typedef struct dnaldpc_output { /* any pointer may be NULL */
@@ -115,12 +115,16 @@ typedef struct dnaldpc_output { /* any pointer may be NULL */
 } dnaldpc_output;
 
 /* Batched replacement of LDPC_Decode -> Run_Belief_Propagation_Decoder (DNA_main.cpp:1572-1575, dec.cpp:583-605)
- * for F independent frames; `max_iter` replaces the global of dec.h:25. HOST buffers; blocking; shards frames
- * over the decoder's devices (no collective: frames are independent). */
+ * for F independent frames; `max_iter` replaces the global of dec.h:25. HOST buffers (pinned or pageable); blocking.
+ * The batch is cut into chunks that the decoder's devices pull from one shared counter (no collective: frames are
+ * independent; the reference's intended split is frames over ranks, DNA_main.cpp:629-651); per device the chunks are
+ * copied in, decoded and copied back concurrently (staging rings in HBM), results land by frame index. */
 int dnaldpc_decode_batch(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter, const dnaldpc_output *out);
 
-/* Same with DEVICE buffers on the decoder's first device, asynchronous on `stream`
- * (outputs are complete when the stream reaches this point; intended for callers that keep data in HBM). */
+/* Same with DEVICE buffers resident on ONE GPU (intended for callers that keep data in HBM). The decoder's first device
+ * works on `stream`; its other devices read the inputs and write the outputs in place through NVLink peer access
+ * (devices without peer access to the buffers are left out), again pulling chunks from one shared counter. Blocks the
+ * host until the batch has drained; outputs are complete when `stream` reaches this point. */
 int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter,
                                 const dnaldpc_output *out, void *stream);
 
@@ -139,6 +143,14 @@ int dnaldpc_run_bp_decoder(dnaldpc_decoder *d, const double *lratio, int max_ite
  * flags: DNALDPC_FLAG_HOST_EXP for libm exp on the host (bit-exact with the reference's exe). */
 int dnaldpc_redecode_sweep(dnaldpc_decoder *d, const double *llr, int64_t F, int max_iter, const double *scales,
                            int n_scales, int flags, const dnaldpc_output *out, int32_t *rounds);
+/* The same sweep for any parameterised input kind: round r decodes with in->param = params[r] (LLR kinds: the scale;
+ * VOTE_I8: eps_r, i.e. LR = exp(k*ln((1-eps_r)/eps_r)) from a fresh 256-entry table per round, which is exactly what the
+ * pipeline's rescaled LLR file holds; BSC_BITS: p_r; AWGN: sigma_r). HOST buffers. The inputs are uploaded ONCE (while
+ * round 0 decodes) and stay in HBM; later rounds run over a device-side list of the rows whose syndrome is still
+ * non-zero, so nothing but that round's results crosses PCIe again. With DNALDPC_FLAG_HOST_EXP (LLR_F64) the failed
+ * frames are exponentiated on the host per round instead (libm exp, bit-exact with the reference's exe). */
+int dnaldpc_redecode_sweep_ex(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter, const double *params,
+                              int n_params, const dnaldpc_output *out, int32_t *rounds);
 
 /* Sliding-window belief propagation for spatially-coupled (SC-LDPC) codes = Run_SW_Decoder (dec.cpp:2092-2196; decoder
  * type 60 of the reference CLI, DNA_main.cpp:1599-1602) with Init_SW_Decoder / Iter_SW_Decoder / Check_Update_SW /
@@ -170,6 +182,18 @@ int dnaldpc_bsc_table(double p, double *table2);                      /* {(1-p)/
  * Keyed by the GLOBAL frame index, so any sharding over GPUs produces the same frames. */
 int dnaldpc_synth_bsc_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
                              int64_t F, double eps, uint32_t *out_bits, void *stream);
+
+/* Received values of a BPSK/AWGN channel (BASELINE configs[3]; channel_AWGN, channel.cpp:23-35): y = (bit ? -1 : +1) +
+ * sigma * n, n = sqrt(-2 ln u1) * cos(2 pi u2) with u1 = ((rng_u64(seed,f,j,4) >> 11) + 1) / 2^53, u2 =
+ * (rng_u64(seed,f,j,5) >> 11) / 2^53 in fp64, rounded to float. out_y: DEVICE float [F][N]. sigma from dnaldpc_std_dev. */
+int dnaldpc_synth_awgn_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
+                              int64_t F, double sigma, float *out_y, void *stream);
+/* Vote counts k = count0 - count1 of aligned reads (BASELINE configs[2]; the soft information of
+ * ex_decoder/decoder.py:292-316): reads per bit c ~ Poisson(mean_reads) capped at 63 (inversion of rng stream 2 against
+ * integer CDF thresholds), each read wrong with probability read_err (streams 3..3+c). out_k: DEVICE int8 [F][N].
+ * Integer arithmetic on the device: identical to the host twin for any sharding. mean_reads in (0, 32]. */
+int dnaldpc_synth_vote_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
+                              int64_t F, double mean_reads, double read_err, int8_t *out_k, void *stream);
 
 /* ---- statistics of the last decode call on this handle ------------------------------------------ */
 typedef struct dnaldpc_stats {

@@ -486,3 +486,36 @@ double orc_rng_normal(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t stre
     double u2 = orc_rng_uniform(seed, frame, bit, stream + 1);
     return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
 }
+
+/* ---------- host twins of the device input generators ---------------------------------------- */
+
+void orc_synth_awgn(const char *cw, uint64_t seed, uint64_t frame, int N, double sigma, float *y) { /* channel.cpp:23-35 */
+    for (int j = 0; j < N; j++) {
+        double n = orc_rng_normal(seed, frame, (uint64_t)j, 4);
+        y[j] = (float)(((cw && cw[j]) ? -1.0 : 1.0) + sigma * n);
+    }
+}
+
+void orc_vote_thresholds(double mean, uint64_t *thr) {
+    double p = exp(-mean), cdf = 0;
+    for (int k = 0; k < 64; k++) {
+        if (k > 0) p = p * mean / k;
+        cdf += p;
+        thr[k] = (uint64_t)((cdf < 1.0 ? cdf : 1.0) * 9007199254740992.0);
+    }
+}
+
+void orc_synth_vote(const char *cw, uint64_t seed, uint64_t frame, int N, double mean_reads, double read_err, signed char *out) {
+    uint64_t thr[64];
+    orc_vote_thresholds(mean_reads, thr);
+    const uint64_t thr_err = (uint64_t)(read_err * 9007199254740992.0);
+    for (int j = 0; j < N; j++) {
+        const uint64_t u = orc_rng_u64(seed, frame, (uint64_t)j, 2) >> 11;
+        int c = 0;
+        while (c < 63 && u >= thr[c]) c++;
+        int wrong = 0;
+        for (int r = 0; r < c; r++) wrong += (orc_rng_u64(seed, frame, (uint64_t)j, 3 + (uint64_t)r) >> 11) < thr_err;
+        const int k = c - 2 * wrong;                     /* count0 - count1 for a 0 bit (decoder.py:292-316) */
+        out[j] = (signed char)((cw && cw[j]) ? -k : k);
+    }
+}

@@ -85,6 +85,12 @@ double orc_rng_uniform(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t str
 /* standard normal via Box-Muller on streams (stream, stream+1) */
 double orc_rng_normal(uint64_t seed, uint64_t frame, uint64_t bit, uint64_t stream);
 
+/* Host twins of the device input generators (dna-ldpc-codes_b200/csrc/bp_kernels.cuh: synth_awgn_kernel,
+ * synth_vote_kernel), one frame: cw = the frame's codeword as N 0/1 chars (NULL = all zero). */
+void orc_synth_awgn(const char *cw, uint64_t seed, uint64_t frame, int N, double sigma, float *y);
+void orc_vote_thresholds(double mean, uint64_t *thr64); /* thr[k] = (uint64)(P(Poisson(mean) <= k) * 2^53), k < 64 */
+void orc_synth_vote(const char *cw, uint64_t seed, uint64_t frame, int N, double mean_reads, double read_err, signed char *k);
+
 #ifdef __cplusplus
 }
 #endif

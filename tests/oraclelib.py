@@ -78,6 +78,8 @@ class Oracle:
             L.orc_rng_uniform.argtypes = [C.c_uint64] * 4
             L.orc_rng_normal.restype = C.c_double
             L.orc_rng_normal.argtypes = [C.c_uint64] * 4
+            L.orc_synth_awgn.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, _fp]
+            L.orc_synth_vote.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double, _cp]
             cls._lib = L
         return cls._lib
 
@@ -217,6 +219,22 @@ def bsc_threshold(eps):
 
 def bsc_flips(seed, frame, n, eps):
     return ((rng_u64(seed, frame, np.arange(n)) >> np.uint64(11)) < bsc_threshold(eps)).astype(np.int8)
+
+
+def synth_awgn(cw, seed, frame, n, sigma):
+    """Host twin of synth_awgn_kernel (oracle/bp_oracle.c:orc_synth_awgn): float32 [n] received values of one frame."""
+    y = np.zeros(n, dtype=np.float32)
+    cwp = None if cw is None else np.ascontiguousarray(cw, dtype=np.int8)
+    Oracle.lib().orc_synth_awgn(None if cwp is None else cwp.ctypes.data, seed, frame, n, sigma, y)
+    return y
+
+
+def synth_vote(cw, seed, frame, n, mean_reads, read_err):
+    """Host twin of synth_vote_kernel (oracle/bp_oracle.c:orc_synth_vote): int8 [n] vote counts of one frame."""
+    k = np.zeros(n, dtype=np.int8)
+    cwp = None if cw is None else np.ascontiguousarray(cw, dtype=np.int8)
+    Oracle.lib().orc_synth_vote(None if cwp is None else cwp.ctypes.data, seed, frame, n, mean_reads, read_err, k)
+    return k
 
 
 class RefLib:
