@@ -137,6 +137,178 @@ def workload_config(args, frames):
             "l2": "inputs larger than L2: message working set %.1f GB per wave vs 126 MB L2" % (min(args.wave, frames) * E * 8 / 1e9)}
 
 
+def _ev_time(torch, fn, reps=1):
+    """CUDA-event time in ms of fn() on the current stream (fn blocks the host until its batch has drained)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
+    """The regimes the headline configuration never exercises (frames that converge: admission, refill-regime check pass,
+    drain-tail compaction; BASELINE configs[2..4]; fp32; min-sum; host buffers of the wide input kinds). A few seconds
+    each, CUDA-event timed after one warm-up pass; frac = B_iter x frame-iterations / time / measured HBM peak."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    W = (N + 31) // 32
+    out = {}
+
+    def run_device(dc, kind, d_in, F, param, max_iter, n_, flags=0, b_iter=B_ITER, reps=1):
+        d_bits = torch.empty((F, (n_ + 31) // 32), dtype=torch.int32, device=dev)
+        d_it = torch.empty(F, dtype=torch.int32, device=dev)
+        d_ok = torch.empty(F, dtype=torch.uint8, device=dev)
+
+        def go():
+            dc.decode_device(kind, d_in.data_ptr(), F, max_iter, param=param, bits_ptr=d_bits.data_ptr(), iters_ptr=d_it.data_ptr(),
+                             ok_ptr=d_ok.data_ptr(), stream=st, flags=flags)
+        go()  # warm-up (slot arrays, queue tables)
+        ms = _ev_time(torch, go, reps)
+        fi = float(d_it.sum().item())
+        return {"frames": F, "ms": ms, "gbit_s": F * n_ / (ms * 1e-3) / 1e9, "frames_per_s": F / (ms * 1e-3),
+                "frame_iters_per_s": fi / (ms * 1e-3), "avg_iters": fi / F, "fer": 1.0 - float(d_ok.float().mean().item()),
+                "whole_step_gbs": b_iter * fi / (ms * 1e-3) / 1e9, "frac": b_iter * fi / (ms * 1e-3) / 1e9 / peak}
+
+    # converging BSC frames (the pipeline's real regime), two batch sizes
+    for F in (65536, 1000000):
+        d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+        dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, 0.006, d_in.data_ptr(), st)
+        out["bsc_eps0.006_%d" % F] = run_device(dec, ldpc.IN_BSC_BITS, d_in, F, 0.006, args.max_iter, N)
+        del d_in
+    # configs[2]: vote counts, 1M frames
+    F = 1000000
+    d_in = torch.empty((F, N), dtype=torch.int8, device=dev)
+    dec.synth_vote_device(d_cw.data_ptr(), 272, args.seed, 0, F, 3.9, 0.01, d_in.data_ptr(), st)
+    out["c3_vote_i8_1000000"] = run_device(dec, ldpc.IN_VOTE_I8, d_in, F, 0.02, args.max_iter, N)
+    # the same frames through the host-buffer call (pinned memory, copies inside the timed region)
+    Fh = 131072
+    h_in = torch.empty((Fh, N), dtype=torch.int8).pin_memory(); h_in.copy_(d_in[:Fh])
+    del d_in
+    out["c3_vote_i8_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_VOTE_I8, h_in, Fh, 0.02, args.max_iter, out["c3_vote_i8_1000000"])
+    del h_in
+    # configs[3]: AWGN at Eb/N0 = 4.6 dB
+    F = 262144
+    sigma = ldpc.std_dev(4.6, 1 - M / N)
+    d_in = torch.empty((F, N), dtype=torch.float32, device=dev)
+    dec.synth_awgn_device(d_cw.data_ptr(), 272, args.seed, 0, F, sigma, d_in.data_ptr(), st)
+    out["c4_awgn_f32_%d" % F] = run_device(dec, ldpc.IN_AWGN_F32, d_in, F, sigma, args.max_iter, N)
+    Fh = 65536
+    h_in = torch.empty((Fh, N), dtype=torch.float32).pin_memory(); h_in.copy_(d_in[:Fh])
+    del d_in
+    out["c4_awgn_f32_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_AWGN_F32, h_in, Fh, sigma, args.max_iter, out["c4_awgn_f32_%d" % F])
+    del h_in
+    # LLR text-file style input: fp64 LLRs, exp on the host with libm (what the CLI does); bound by libm exp on the host cores
+    Fh = 16384
+    d_b = torch.empty((Fh, W), dtype=torch.int32, device=dev)
+    dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, Fh, 0.006, d_b.data_ptr(), st)
+    torch.cuda.synchronize()
+    bits = np.unpackbits(d_b.cpu().numpy().view(np.uint8).reshape(Fh, W * 4), axis=1, bitorder="little")[:, :N]
+    L = float(np.log((1 - 0.006) / 0.006))
+    h_llr = torch.from_numpy(np.where(bits == 0, L, -L)).pin_memory()
+    del d_b, bits
+    out["llr_f64_host_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None, flags=ldpc.FLAG_HOST_EXP)
+    out["llr_f64_device_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None)
+    del h_llr
+    # min-sum and fp32 at the headline operating point (no frame converges: pure kernel throughput)
+    F = 16384
+    d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+    dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, args.eps, d_in.data_ptr(), st)
+    out["minsum_eps%g_%d" % (args.eps, F)] = run_device(dec, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, flags=ldpc.FLAG_MINSUM)
+    d32 = ldpc.Decoder(code, devices=[torch.cuda.current_device()], wave_frames=args.wave, precision=ldpc.PREC_F32)
+    out["fp32_eps%g_%d" % (args.eps, F)] = run_device(d32, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, b_iter=0.5 * B_ITER)
+    d32.close()
+    del d_in
+    # configs[4]: Neal-style random regular code n=65536, column weight 3, rate 0.9
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_regular_pchk
+    n5, m5 = 65536, 6554
+    row_ptr, col_idx = gen_regular_pchk.gen_regular(n5, m5, 3, 5)
+    code5 = ldpc.Code(csr=(m5, n5, row_ptr, col_idx))
+    dec5 = ldpc.Decoder(code5, devices=[torch.cuda.current_device()], wave_frames=args.wave)
+    b5 = 32 * code5.E + 8.25 * n5
+    for eps5, F5 in ((0.02, 8192), (0.004, 32768)):
+        d_in = torch.empty((F5, n5 // 32), dtype=torch.int32, device=dev)
+        dec5.synth_bsc_device(None, 0, args.seed, 0, F5, eps5, d_in.data_ptr(), st)  # all-zero codeword
+        out["c5_n65536_eps%g_%d" % (eps5, F5)] = run_device(dec5, ldpc.IN_BSC_BITS, d_in, F5, eps5, 50, n5, b_iter=b5)
+        del d_in
+    dec5.close()
+    return out
+
+
+def host_leg(ldpc, torch, dec, kind, h_in, F, param, max_iter, device_ref, flags=0):
+    """One host-buffer batch through dnaldpc_decode_batch (pinned memory; H2D and D2H inside the timed region)."""
+    Cc = ldpc.C
+    W = (N + 31) // 32
+    h_bits = torch.empty((F, W), dtype=torch.int32).pin_memory()
+    h_it = torch.empty(F, dtype=torch.int32).pin_memory()
+    h_ok = torch.empty(F, dtype=torch.uint8).pin_memory()
+    inp = ldpc.Input(kind=kind, flags=flags, data=h_in.data_ptr(), frame_stride=0, param=param, table=None)
+    outp = ldpc.Output(bits=h_bits.data_ptr(), dblk=None, iters=h_it.data_ptr(), is_codeword=h_ok.data_ptr(), posterior=None, pchk=None)
+
+    def go():
+        rc = ldpc.lib().dnaldpc_decode_batch(dec._h, Cc.byref(inp), F, max_iter, Cc.byref(outp))
+        if rc:
+            raise RuntimeError(ldpc.lib().dnaldpc_last_error())
+    go()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    go()
+    dt = time.perf_counter() - t0
+    fi = float(h_it.sum().item())
+    h2d = h_in.numel() * h_in.element_size()
+    r = {"frames": F, "ms": dt * 1e3, "gbit_s": F * N / dt / 1e9, "frames_per_s": F / dt, "frame_iters_per_s": fi / dt,
+         "avg_iters": fi / F, "h2d_bytes": h2d, "d2h_bytes": F * (W * 4 + 5), "pcie_gbs": (h2d + F * (W * 4 + 5)) / dt / 1e9}
+    if device_ref is not None:
+        r["vs_device_resident"] = r["frames_per_s"] / device_ref["frames_per_s"]
+    return r
+
+
+def inproc_multi(ldpc, torch, code, d_cw_np, args, world):
+    """Rank 0 alone decodes ONE batch through the library's own multi-GPU dispatch (dnaldpc_config.devices[0..N)), host
+    buffers, against the same call on one device. The other ranks have released their decoders and wait on the store."""
+    F = args.inproc_frames
+    W = (N + 31) // 32
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    one = ldpc.Decoder(code, devices=[0], wave_frames=args.wave)
+    d_cw = torch.from_numpy(d_cw_np).to(dev)
+    d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+    one.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, 0.006, d_in.data_ptr(), st)
+    h_in = torch.empty((F, W), dtype=torch.int32).pin_memory(); h_in.copy_(d_in)
+    del d_in
+    res = {}
+    outs = []
+    for name, devs in (("one", [0]), ("many", list(range(world)))):
+        dec = one if name == "one" else ldpc.Decoder(code, devices=devs, wave_frames=args.wave)
+        h_bits = torch.empty((F, W), dtype=torch.int32).pin_memory()
+        h_it = torch.empty(F, dtype=torch.int32).pin_memory()
+        h_ok = torch.empty(F, dtype=torch.uint8).pin_memory()
+        inp = ldpc.Input(kind=ldpc.IN_BSC_BITS, flags=0, data=h_in.data_ptr(), frame_stride=0, param=0.006, table=None)
+        outp = ldpc.Output(bits=h_bits.data_ptr(), dblk=None, iters=h_it.data_ptr(), is_codeword=h_ok.data_ptr(), posterior=None, pchk=None)
+        best = None
+        for rep in range(3):  # first pass warms up (slot arrays and staging rings on every device)
+            t0 = time.perf_counter()
+            rc = ldpc.lib().dnaldpc_decode_batch(dec._h, ldpc.C.byref(inp), F, args.max_iter, ldpc.C.byref(outp))
+            dt = time.perf_counter() - t0
+            if rc:
+                raise RuntimeError(ldpc.lib().dnaldpc_last_error())
+            if rep > 0:
+                best = dt if best is None else min(best, dt)
+        res[name] = best
+        outs.append((h_bits, h_it, h_ok))
+        dec.close()
+    same = all(bool(torch.equal(a, b)) for a, b in zip(outs[0], outs[1]))
+    fi = float(outs[0][1].sum().item())
+    return {"workload": "one batch of %d frames, BSC eps=0.006, max %d iterations, host buffers, rank 0 only" % (F, args.max_iter),
+            "devices": world, "gbit_s": F * N / res["many"] / 1e9, "frame_iters_per_s": fi / res["many"],
+            "one_device_gbit_s": F * N / res["one"] / 1e9, "speedup_vs_1": res["one"] / res["many"],
+            "efficiency": res["one"] / res["many"] / world, "identical_to_one_device": same}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,6 +412,17 @@ def run_ours(args):
     e2e_val = world * F * e2e_steps * N / float(te[0]) / 1e9
     same = bool((h_it.to(dev) == d_it).all()) and bool((h_bits.to(dev) == d_bits).all())
 
+    # ---- N > 1: the library's own multi-GPU dispatch is driven by rank 0 alone, later on; the other ranks free their
+    # GPUs and wait on the store (no NCCL kernel is involved)
+    want_inproc = world > 1 and args.inproc_frames > 0
+    store = dist.distributed_c10d._get_default_store() if want_inproc else None
+    if rank != 0 and want_inproc:
+        import datetime
+        del d_in, d_bits, d_it, d_ok, h_in, h_bits, h_it, h_ok, d_cw
+        dec.close()
+        torch.cuda.empty_cache()
+        store.set("released_%d" % rank, "1")
+        store.wait(["inproc_done"], datetime.timedelta(seconds=3000))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,8 +463,25 @@ def run_ours(args):
         except Exception:
             pass
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak)
+
+    inproc = None
+    if want_inproc:
+        import datetime
+        del d_in, d_bits, d_it, d_ok, h_in, h_bits, h_it, h_ok, d_cw
+        dec.close()
+        torch.cuda.empty_cache()
+        try:
+            store.wait(["released_%d" % r for r in range(1, world)], datetime.timedelta(seconds=600))
+            inproc = inproc_multi(ldpc, torch, code, cw, args, world)
+        except Exception as ex:  # reported, never fatal for the headline line
+            inproc = {"error": repr(ex)}
+        store.set("inproc_done", "1")
+
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         info = cpu_reference_run(args.ref_frames_per_core, args.eps, args.max_iter)
         cpu = {"value": info["frames"] * N / info["decode_s"] / 1e9, "unit": "Gbit/s", "cores": info["cores"], "kind": info["kind"],
                "sample": "%d frames (%d per core, one pinned process per core) x max %d iterations, eps=%g; %.2f ms per iteration per core"
@@ -297,6 +497,10 @@ def run_ours(args):
                 "steps": e2e_steps, "matches_device_path": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
+    if secondary is not None:
+        line["secondary"] = secondary
+    if inproc is not None:
+        line["inproc_multi"] = inproc
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -333,9 +537,11 @@ def main():
     ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--wave", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=7)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-frames-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary regimes (converging frames, configs 3-5, fp32, min-sum, host-buffer kinds)")
+    ap.add_argument("--inproc-frames", type=int, default=1000000, help="N > 1: frames of the one batch rank 0 decodes through the library's own multi-GPU dispatch")
     ap.add_argument("--alg", default="bp", choices=["bp", "minsum"], help="bp = sum-product (the metric); minsum = floating min-sum (SURVEY 8f-4)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = bit-exact mode (the metric); f32 = optional fast mode")
     args = ap.parse_args()

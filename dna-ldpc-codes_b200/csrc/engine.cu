@@ -408,10 +408,11 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
             // steady state = every slot busy and nobody being admitted (e.g. long-running frames)
             steady_ = last_admitted == 0 && last_inuse >= (unsigned)S;
             if (!final && last_inuse == 0 && admitted_total == published()) {
-                // idle engine, starved source: do not spin empty ticks
+                // Idle engine, starved source: do not spin empty ticks. The check / bit passes below still run: this tick's
+                // admission kernels are already queued and may pick up frames published meanwhile, and a slot's fresh mark
+                // is only valid until the next tick's admission.
                 src.wait_for_frames();
                 last_admitted = 1;  // look for frames in the next tick
-                continue;
             }
             if (!no_compact && !profiling && final && admitted_total == published() && packed_cap >= 2 * kFG &&
                 (long long)last_inuse * 100 <= packed_cap * compact_pct) {

@@ -186,12 +186,18 @@ class HostSource : public FrameSource {
         bool bounce_used[2] = {false, false};
         for (;;) {
             const int64_t need = q + b_.chunk;
+            // Nothing left to claim: say so at once. The engine starts compacting its drain tail when the source is
+            // final, and room in the rings may be a long time coming (it waits for the frames that run to max_iter).
+            auto none_left = [&] { return b_.next_chunk.load(std::memory_order_relaxed) >= b_.n_chunks; };
+            if (none_left()) break;
             if (keep_) {
                 if (need > in_ring_) break;  // this engine's resident buffers are full: the other engines take the rest
             } else {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return abort_ || (need <= admitted_ + in_ring_ && need <= retired_ + out_ring_); });
+                while (!(abort_ || none_left() || (need <= admitted_ + in_ring_ && need <= retired_ + out_ring_)))
+                    cv_.wait_for(lk, std::chrono::milliseconds(1));  // another engine may take the last chunk meanwhile
             }
+            if (none_left()) break;
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 if (abort_) return;
