@@ -249,7 +249,8 @@ __device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_la
 // warp lands the contiguous run in the warp's tile, the factors d_k overwrite the tile in place, and only the 9
 // check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
 // <= 168 registers: 12 warps (3 CTAs, 3 x 73.8 KB of shared memory) per SM instead of 8, i.e. 50 % more bytes in flight.
-// Groups with a slot that starts a frame or with idle slots fill the tile lane by lane with cp.async instead.
+// Groups with slots that start a frame overwrite those lanes' columns of the tile with a warp-cooperative gather of the
+// channel ratios (below); idle lanes ride along in the bulk copy and are skipped.
 // EXACT = false (irregular rows of degree <= DC): the bulk copy takes the row's deg x 256 bytes; the tile stays DC rows.
 template <typename T, int DC, bool EXACT = true>
 __global__ void __launch_bounds__(kRowWarps * 32, EXACT ? 3 : 6)
@@ -273,30 +274,69 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
     T *base = msg + ((size_t)g * E + e0) * kFG + lane;
     T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
     const T *lr_lane = lratio + (size_t)g * N * kFG + lane;
-    if (act == 0xffffffffu && fw == 0) {  // warp-uniform: full group, nobody starts a frame -> one bulk copy
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_fence_init();
-            mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
-            tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar);
-        }
+    // Lanes that carry on with a frame take their messages from the tile: ONE bulk copy lands the check's whole
+    // contiguous run (the columns of starting / idle lanes come along and are ignored or overwritten below).
+    const uint32_t fresh_mask = fw & act;
+    const bool streaming = (act & ~fresh_mask) != 0;  // warp-uniform
+    if (streaming && lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
+        tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar);
+    }
+    if (fresh_mask == 0) {
         __syncwarp();
         mbar_wait(bar, 0);
     } else {
-        // Mixed group: every active lane fills its own column with asynchronous 8-byte copies (cp.async / LDGSTS): a
-        // slot that starts a frame takes the channel ratios of the check's bits (Init_Belief_Propagation), the others
-        // their messages; finished / empty lanes copy nothing. All DC copies of a lane are in flight at once and, as
-        // with the bulk copy, none of them occupies a register.
-        if (!on) return;
-#pragma unroll 12
-        for (int k = 0; k < DC; k++) {
-            if (!EXACT && k >= deg) break;
-            const T *src = fresh ? lr_lane + (size_t)__ldg(col_idx + e0 + k) * kFG : base + (size_t)k * kFG;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(col + k * kFG)), "l"(src), "n"(sizeof(T)) : "memory");
+        // Lanes that start a frame need the channel ratios of the check's bits instead (Init_Belief_Propagation): the
+        // WHOLE warp gathers them, lane = (edge of a block of 32 / R edges, rank r among the starting lanes) - with the
+        // usual handful of starting lanes 18 loads per lane for the 72 edges instead of one divergent load per edge.
+        const int nf = __popc(fresh_mask);
+        const T *lr_base = lratio + (size_t)g * N * kFG;
+        if (nf <= 8) {
+            constexpr int NT = (DC + 3) / 4;
+            const int r = lane & 7, kq = lane >> 3;
+            const bool mine = r < nf;
+            const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
+            // Column indices, then the ratios themselves into registers: both are in flight together with the bulk copy
+            // (the registers are free here: the arithmetic's working set is not live yet). Once the bulk copy has
+            // landed they overwrite the starting lanes' columns of the tile.
+            int idx[NT];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                const int k = t * 4 + kq;
+                idx[t] = (mine && k < deg) ? __ldg(col_idx + e0 + k) : -1;
+            }
+            T v[NT];
+#pragma unroll
+            for (int t = 0; t < NT; t++) v[t] = idx[t] >= 0 ? lr_base[(size_t)idx[t] * kFG + f] : T(0);
+            __syncwarp();
+            if (streaming) mbar_wait(bar, 0);
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                const int k = t * 4 + kq;
+                if (idx[t] >= 0) tile[k * kFG + f] = v[t];
+            }
+        } else {  // many starting lanes (the first ticks of a batch): R = 16 or 32 ranks per instruction
+            const int lg = nf <= 16 ? 4 : 5, R = 1 << lg, per = 32 >> lg;
+            const int r = lane & (R - 1), kq = lane >> lg;
+            const bool mine = r < nf;
+            const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
+            __syncwarp();
+            if (streaming) mbar_wait(bar, 0);
+#pragma unroll 6
+            for (int k0 = 0; k0 < deg; k0 += per) {
+                const int k = k0 + kq;
+                if (mine && k < deg)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(tile + k * kFG + f)),
+                                 "l"(lr_base + (size_t)__ldg(col_idx + e0 + k) * kFG + f), "n"(sizeof(T)) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
+    if (!on) return;  // finished / empty slots keep their messages untouched
     smem_row_compute<T, DC, EXACT>(col, base, lr_lane, col_idx + e0, fresh, deg);
 }
 

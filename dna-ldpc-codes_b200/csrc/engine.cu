@@ -152,8 +152,10 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         else row_pass_kernel<T, DC, EX, ALG_BP><<<grid, kRowWarps * 32, 0, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);         \
     } while (0)
     static const bool no_smem = getenv("DNALDPC_ROW_REGS") != nullptr;  // A/B switch: register-resident check kernel
-    static const bool always_smem = getenv("DNALDPC_ROW_SMEM_ALWAYS") != nullptr;  // A/B switch
-    if (!no_smem && (steady_ || always_smem) && reg_rows_ && max_row_deg_ == 72 && !minsum_ && sizeof(T) == 8) {
+    // A/B switch: the round-1 policy (smem-staged kernel only in ticks where every slot is busy and nobody is admitted)
+    static const bool steady_only = getenv("DNALDPC_ROW_SMEM_STEADY_ONLY") != nullptr;
+    const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && sizeof(T) == 8;
+    if (use_smem && reg_rows_ && max_row_deg_ == 72) {
         // the (.,72)-regular sum-product hot path: check messages staged in shared memory by TMA, 12 warps per SM
         const size_t smem = (size_t)kRowWarps * 72 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
         bool &attr_set = smem_attr_set_[sizeof(T) == 4];
@@ -162,7 +164,7 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
             attr_set = true;
         }
         row_pass_smem_kernel<T, 72><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);
-    } else if (!no_smem && (steady_ || always_smem) && max_row_deg_ <= 32 && max_row_deg_ > 8 && !minsum_ && sizeof(T) == 8) {
+    } else if (use_smem && max_row_deg_ <= 32 && max_row_deg_ > 8) {
         // irregular rows of degree <= 32 (e.g. the n=65536 column-weight-3 code): same staging, deg x 256 B bulk copies
         const size_t smem = (size_t)kRowWarps * 32 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
         row_pass_smem_kernel<T, 32, false><<<grid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G);
