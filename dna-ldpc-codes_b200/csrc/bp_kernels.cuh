@@ -201,6 +201,18 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Same with an L2 evict-first policy: the message stream is read once per pass and should not push out the few lines
+// that ARE reused inside a pass (the channel ratios gathered by lanes that start a frame: 8 checks per bit).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 // Arithmetic of one (check, slot) whose DC inputs sit in the lane's column of a shared-memory tile (col[k * 32]):
 // pass 1, descending: d_k in place, backward products check-pointed every 8 edges; pass 2: lr_k streamed to `base`.
 // EXACT = false: rows of any degree deg <= DC (irregular codes); the padding edges k >= deg are exact identities in
@@ -338,6 +350,300 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
     }
     if (!on) return;  // finished / empty slots keep their messages untouched
     smem_row_compute<T, DC, EXACT>(col, base, lr_lane, col_idx + e0, fresh, deg);
+}
+
+// Persistent form of the shared-memory check pass. 3 CTAs x 4 warps stay resident per SM and pull JOBS from a device
+// counter: a job is one check i for a block of `gblock` consecutive groups. Per job the warp stages the check's column
+// indices in shared memory once, so the channel-ratio gather of the lanes that start a frame no longer waits for an
+// index load in every item (in the one-item-per-warp kernel that dependent pair of loads outlasts the 18 KB bulk copy
+// and sets the time a tile stays occupied); the slot masks of the next group are fetched while the current one is
+// worked on; and a tile is refilled as soon as ITS warp is done instead of when the last of the 4 warps of a CTA is.
+// One mbarrier per warp, phase-toggled; the tile is handed back to the async proxy with a proxy fence.
+template <typename T, int DC, bool EXACT = true>
+__global__ void __launch_bounds__(kRowWarps * 32, EXACT ? 3 : 6)
+row_pass_persist_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
+                        const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr,
+                        const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G, int gblock,
+                        unsigned int *__restrict__ job_counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRowWarps * DC * kFG * sizeof(T)) + warp;
+    int *sidx = reinterpret_cast<int *>(smem_raw + (size_t)kRowWarps * DC * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t)) + warp * DC;
+    T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    const int nblk = (G + gblock - 1) / gblock;
+    const unsigned njobs = (unsigned)M * (unsigned)nblk;
+    for (;;) {
+        unsigned job = 0;
+        if (lane == 0) job = atomicAdd(job_counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) break;
+        const int gb = (int)(job / (unsigned)M), i = (int)(job - (unsigned)gb * (unsigned)M);
+        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
+        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
+        for (int k = lane; k < deg; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
+        __syncwarp();
+        int g = g0 + gb * gblock;
+        const int gend = min(g0 + G, g + gblock);
+        uint32_t act = actw[g], fw = freshw[g];
+        for (; g < gend; g++) {
+            uint32_t act_next = 0, fw_next = 0;
+            if (g + 1 < gend) { act_next = actw[g + 1]; fw_next = freshw[g + 1]; }  // in flight during this group's work
+            if (act != 0) {
+                const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
+                T *base = msg + ((size_t)g * E + e0) * kFG + lane;
+                const T *lr_base = lratio + (size_t)g * N * kFG;
+                const uint32_t fresh_mask = fw & act;
+                const bool streaming = (act & ~fresh_mask) != 0;  // warp-uniform
+                if (streaming && lane == 0) {
+                    mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
+                    tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar);
+                }
+                if (fresh_mask == 0) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                } else {
+                    // starting lanes: channel ratios of the check's bits, gathered by the whole warp, 8 ranks x 4 edges
+                    // per load instruction; the first 8 ranks travel together with the bulk copy
+                    constexpr int NT = (DC + 3) / 4;
+                    const int nf = __popc(fresh_mask);
+                    const int kq = lane >> 3;
+                    for (int r0 = 0; r0 < nf; r0 += 8) {
+                        const int r = r0 + (lane & 7);
+                        const bool mine = r < nf;
+                        const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
+                        T v[NT];
+#pragma unroll
+                        for (int t = 0; t < NT; t++) {
+                            const int k = t * 4 + kq;
+                            v[t] = (mine && k < deg) ? lr_base[(size_t)sidx[k] * kFG + f] : T(0);
+                        }
+                        if (r0 == 0 && streaming) {
+                            mbar_wait(bar, phase);
+                            phase ^= 1u;
+                        }
+#pragma unroll
+                        for (int t = 0; t < NT; t++) {
+                            const int k = t * 4 + kq;
+                            if (mine && k < deg) tile[k * kFG + f] = v[t];
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (on) smem_row_compute<T, DC, EXACT>(col, base, lr_base + lane, col_idx + e0, fresh, deg);
+                __syncwarp();  // every lane is done with the tile
+                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the next bulk write
+            }
+            act = act_next; fw = fw_next;
+        }
+    }
+}
+
+// ---- tensor memory (tcgen05) as a second on-chip tile ----------------------------------------------------
+// The check pass is bound by the bytes it can keep in flight per SM: 12 shared-memory tiles of 18 KB, each either being
+// filled or being worked on. The 256 KB of tensor memory per SM are idle in this kernel (no MMA anywhere), so the factors
+// d_k of a check are parked THERE after pass 1 (tcgen05.st, 144 of a lane's 512 32-bit columns; three warps share a
+// lane quarter) and read back block by block in pass 2 (tcgen05.ld): the shared-memory tile is free again after one
+// third of the arithmetic and the bulk copy of the warp's NEXT check is in flight during the other two thirds.
+__device__ __forceinline__ void tmem_alloc_512(uint32_t *smem_slot) {  // one full warp; writes the base address to smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {  // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512u) : "memory");
+}
+// 8 doubles of this lane <-> 16 consecutive 32-bit columns of the lane's tensor-memory row
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const double (&d)[8]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[2 * i] = (uint32_t)__double2loint(d[i]); w[2 * i + 1] = (uint32_t)__double2hiint(d[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(w[0]),"r"(w[1]),"r"(w[2]),"r"(w[3]),"r"(w[4]),"r"(w[5]),"r"(w[6]),"r"(w[7]),"r"(w[8]),"r"(w[9]),"r"(w[10]),"r"(w[11]),"r"(w[12]),"r"(w[13]),"r"(w[14]),"r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, double (&d)[8]) {
+    uint32_t w[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(w[0]),"=r"(w[1]),"=r"(w[2]),"=r"(w[3]),"=r"(w[4]),"=r"(w[5]),"=r"(w[6]),"=r"(w[7]),"=r"(w[8]),"=r"(w[9]),"=r"(w[10]),"=r"(w[11]),"=r"(w[12]),"=r"(w[13]),"=r"(w[14]),"=r"(w[15]) : "r"(taddr) : "memory");
+    // the registers are valid after the wait: tie them to it so that no use can be scheduled ahead of it
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(w[0]),"+r"(w[1]),"+r"(w[2]),"+r"(w[3]),"+r"(w[4]),"+r"(w[5]),"+r"(w[6]),"+r"(w[7]),"+r"(w[8]),"+r"(w[9]),"+r"(w[10]),"+r"(w[11]),"+r"(w[12]),"+r"(w[13]),"+r"(w[14]),"+r"(w[15]) :: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+}
+
+constexpr int kTmWarps = 12;  // one CTA per SM: 12 tiles of shared memory, 3 warps per tensor-memory lane quarter
+
+// Persistent check pass, fp64, regular rows of degree DC (multiple of 8): jobs (check i, block of `gblock` groups) from
+// a device counter like row_pass_persist_kernel. Between pass 1 and pass 2 of an item the warp already starts its NEXT
+// item (the next group of the job, or the first group of the next job): the bulk copy into the freed tile and, when
+// lanes of that group start a frame, the first 8 ranks of their channel-ratio gather into registers that stay in
+// flight during pass 2.
+template <int DC>
+__global__ void __launch_bounds__(kTmWarps * 32, 1)
+row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio, const uint32_t *__restrict__ actw,
+                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
+                     int g0, int G, int gblock, unsigned int *__restrict__ job_counter, int l2_hint) {
+    static_assert(DC % 8 == 0 && 2 * DC * (kTmWarps / 4) <= 512, "tensor-memory columns");
+    constexpr int NB = DC / 8, NT = DC / 4;
+    const uint64_t policy = l2_evict_first_policy();
+    constexpr uint32_t kTileBytes = DC * kFG * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *tile = reinterpret_cast<double *>(smem_raw) + (size_t)warp * DC * kFG;
+    unsigned char *aux = smem_raw + (size_t)kTmWarps * DC * kFG * sizeof(double);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(aux) + warp;
+    int *sidx = reinterpret_cast<int *>(aux + kTmWarps * sizeof(uint64_t)) + warp * DC;
+    uint32_t *tm_slot = reinterpret_cast<uint32_t *>(aux + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * DC * sizeof(int));
+    const double *col = tile + lane;
+    if (warp == 0) tmem_alloc_512(tm_slot);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = *tm_slot;
+    // this warp's rows: lane quarter (warp % 4) - the only one its tcgen05.ld / st can reach - and a private column range
+    const uint32_t taddr = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 2 * DC);
+    const int nblk = (G + gblock - 1) / gblock;
+    const unsigned njobs = (unsigned)M * (unsigned)nblk;
+    const int kq = lane >> 3, rk = lane & 7;
+    uint32_t phase = 0;
+
+    // a job's first item: (check, first group); false when the counter has run out. Restages the column indices.
+    auto fetch_job = [&](int &g, int &gend, int &e0) -> bool {
+        unsigned job = 0;
+        if (lane == 0) job = atomicAdd(job_counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) return false;
+        const int jb = (int)(job / (unsigned)M), i = (int)(job - (unsigned)jb * (unsigned)M);
+        g = g0 + jb * gblock;
+        gend = min(g0 + G, g + gblock);
+        e0 = i * DC;
+        __syncwarp();  // nobody still reads the previous job's indices
+        for (int k = lane; k < DC; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
+        __syncwarp();
+        return true;
+    };
+    // starts an item: bulk copy of its messages (if any lane carries on) and ranks 0..7 of the starting lanes' gather
+    auto start_item = [&](int g, int e0, uint32_t act, uint32_t fw, double (&v)[NT]) {
+        const uint32_t fresh_mask = fw & act;
+        if ((act & ~fresh_mask) != 0 && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses to the tile before the bulk write
+            mbar_expect_tx(bar, kTileBytes);
+            if (l2_hint) tma_load_1d_hint(tile, msg + ((size_t)g * E + e0) * kFG, kTileBytes, bar, policy);
+            else tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, kTileBytes, bar);
+        }
+        if (fresh_mask != 0) {
+            const bool mine = rk < __popc(fresh_mask);
+            const int f = mine ? (int)__fns(fresh_mask, 0, rk + 1) : 0;
+            const double *lr_base = lratio + (size_t)g * N * kFG;
+#pragma unroll
+            for (int t = 0; t < NT; t++) v[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
+        }
+    };
+
+    int g = 0, gend = 0, e0 = 0;
+    bool valid = fetch_job(g, gend, e0);
+    uint32_t act = 0, fw = 0;
+    double v[NT];
+    if (valid) {
+        act = actw[g]; fw = freshw[g];
+        if (act != 0) start_item(g, e0, act, fw, v);
+    }
+    while (valid) {
+        uint32_t act_n = 0, fw_n = 0;
+        if (g + 1 < gend) { act_n = actw[g + 1]; fw_n = freshw[g + 1]; }  // in flight during pass 1
+        const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
+        double *base = msg + ((size_t)g * E + e0) * kFG + lane;
+        const int e0_cur = e0, g_cur = g;
+        double ck[NB];
+        bool bad = false;
+        if (act != 0) {
+            const uint32_t fresh_mask = fw & act;
+            if ((act & ~fresh_mask) != 0) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+            if (fresh_mask != 0) {  // the gathered ratios overwrite the starting lanes' columns of the landed tile
+                const int nf = __popc(fresh_mask);
+                const double *lr_base = lratio + (size_t)g * N * kFG;
+                {
+                    const bool mine = rk < nf;
+                    const int f = mine ? (int)__fns(fresh_mask, 0, rk + 1) : 0;
+#pragma unroll
+                    for (int t = 0; t < NT; t++)
+                        if (mine) tile[(t * 4 + kq) * kFG + f] = v[t];
+                }
+                for (int r0 = 8; r0 < nf; r0 += 8) {  // more than 8 starting lanes (first ticks of a batch): further rounds, not overlapped
+                    const int r = r0 + rk;
+                    const bool mine = r < nf;
+                    const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
+                    double w[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; t++) w[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
+#pragma unroll
+                    for (int t = 0; t < NT; t++)
+                        if (mine) tile[(t * 4 + kq) * kFG + f] = w[t];
+                }
+                __syncwarp();
+            }
+            // pass 1, descending: d_k to tensor memory, backward products check-pointed every 8 edges
+            double B = 1.0;
+#pragma unroll
+            for (int b = NB - 1; b >= 0; b--) {
+                double d8[8];
+#pragma unroll
+                for (int kk = 7; kk >= 0; kk--) {
+                    const double dk = check_factor(col[(b * 8 + kk) * kFG], bad);
+                    d8[kk] = dk;
+                    if (kk == 7) ck[b] = B;
+                    B = mul_rn(B, dk);
+                }
+                tmem_st8(taddr + (uint32_t)(b * 16), d8);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            __syncwarp();  // every lane has read its column: the tile can take the next check
+        }
+        // the successor: next group of this job, or the first group of the next job
+        if (g + 1 < gend) { g++; act = act_n; fw = fw_n; }
+        else {
+            valid = fetch_job(g, gend, e0);
+            if (valid) { act = actw[g]; fw = freshw[g]; }
+        }
+        if (valid && act != 0) start_item(g, e0, act, fw, v);
+        // (only `on`, `fresh`, `base`, `bad`, `ck`, `g_cur`, `e0_cur` still belong to the current item from here on)
+        if (on && bad) row_slow_path<double>(base, lratio + (size_t)g_cur * N * kFG + lane, col_idx + e0_cur, DC, fresh);  // invalid ratios: full IEEE divisions
+        // pass 2, ascending: factors back from tensor memory, lr_k streamed to the message array
+        if (__any_sync(0xffffffffu, on)) {
+            double F = 1.0;
+            const bool store = on && !bad;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                double d8[8], Bv[8];
+                tmem_ld8(taddr + (uint32_t)(b * 16), d8);
+                Bv[7] = ck[b];
+#pragma unroll
+                for (int kk = 7; kk > 0; kk--) Bv[kk - 1] = mul_rn(Bv[kk], d8[kk]);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    const double t = mul_rn(F, Bv[kk]);
+                    const double lr = check_to_bit(t);
+                    if (store) st_stream(base + (size_t)(b * 8 + kk) * kFG, lr);
+                    F = mul_rn(F, d8[kk]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tm_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -561,6 +867,7 @@ struct SynArgs {
     unsigned int *finished;         // += frames that finished in this launch
     unsigned int *counters_to_zero; // ring entry (kCounterWords words) re-armed for a later tick, or NULL
     int clear_fresh;                // tick without admission: no assign_kernel will reset the fresh marks
+    unsigned int *row_jobs;         // job counter of the persistent check-pass kernel, re-armed for this tick's launch
 };
 
 constexpr int kCounterWords = 4;    // per tick: slots in use, frames admitted, frames finished, low-water q (armed to ~0)
@@ -571,6 +878,7 @@ __device__ __forceinline__ uint32_t syn_head(const SchedArrays &s, const SynArgs
     if (a.counters_to_zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         a.counters_to_zero[0] = 0; a.counters_to_zero[1] = 0; a.counters_to_zero[2] = 0; a.counters_to_zero[3] = 0xffffffffu;
     }
+    if (a.row_jobs && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.row_jobs = 0;
     act = s.actw[g];
     const uint32_t consider = a.consider_new ? s.newfw[g] : act;
     if (consider == 0 && a.counter && blockIdx.x == 0 && threadIdx.x == 0) {

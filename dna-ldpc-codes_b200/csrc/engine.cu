@@ -64,7 +64,7 @@ Engine::Engine(const Code &code, int device, int precision, int wave_frames)
     up(&d_col_edge_, code.col_edge);
     chk(cudaMalloc((void **)&d_table_, 256 * sizeof(double)), "cudaMalloc(table)");
     chk(cudaMalloc((void **)&d_next_, 3 * sizeof(unsigned long long)), "cudaMalloc(next)");
-    chk(cudaMalloc((void **)&d_counters_, (size_t)kRing * kCounterWords * sizeof(unsigned)), "cudaMalloc(counters)");
+    chk(cudaMalloc((void **)&d_counters_, ((size_t)kRing * kCounterWords + 1) * sizeof(unsigned)), "cudaMalloc(counters)");  // + the check pass's job counter
     chk(cudaMallocHost((void **)&h_counters_, (size_t)kRing * kCounterWords * sizeof(unsigned)), "cudaMallocHost(counters)");
     chk(cudaEventCreateWithFlags(&ready_ev_, cudaEventDisableTiming), "cudaEventCreate");
     chk(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_), "cudaDeviceGetAttribute");
@@ -155,7 +155,42 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     // A/B switch: the round-1 policy (smem-staged kernel only in ticks where every slot is busy and nobody is admitted)
     static const bool steady_only = getenv("DNALDPC_ROW_SMEM_STEADY_ONLY") != nullptr;
     const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && sizeof(T) == 8;
-    if (use_smem && reg_rows_ && max_row_deg_ == 72) {
+    static const bool no_persist = getenv("DNALDPC_ROW_PERSIST") == nullptr;  // A/B switch: persistent form (measured: no gain)
+    static const int gblock = getenv("DNALDPC_ROW_GBLOCK") ? std::max(1, atoi(getenv("DNALDPC_ROW_GBLOCK"))) : 8;
+    // Tensor memory as the second on-chip tile (row_pass_tmem_kernel): the default for the (.,72)-regular fp64 code.
+    // A/B switches: DNALDPC_ROW_NO_TMEM=1 -> the one-item-per-warp shared-memory kernel; job size and L2 policy of the
+    // bulk copies (measured: one group per job keeps the gathered channel-ratio lines of a group in L2 between the 8
+    // checks that use a bit, 1.81 ms per refill-regime launch against 1.88 / 2.15 ms with 4 / 8 groups per job).
+    static const bool use_tmem = getenv("DNALDPC_ROW_NO_TMEM") == nullptr;
+    static const int tm_gblock = getenv("DNALDPC_ROW_GBLOCK") ? gblock : 1;
+    static const int tm_hint = getenv("DNALDPC_ROW_L2HINT") ? atoi(getenv("DNALDPC_ROW_L2HINT")) : 1;
+    if (use_smem && use_tmem && reg_rows_ && max_row_deg_ == 72) {
+        // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
+        const size_t smem = (size_t)kTmWarps * 72 * kFG * sizeof(double) + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * 72 * sizeof(int) + 16;
+        if (!tmem_attr_set_) {
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tmem_attr_set_ = true;
+        }
+        const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
+        unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
+        row_pass_tmem_kernel<72><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, std::min(tm_gblock, G), jobs, tm_hint);
+    } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
+        // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
+        const bool big = reg_rows_ && max_row_deg_ == 72;
+        const int dc = big ? 72 : 32;
+        const size_t smem = (size_t)kRowWarps * dc * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t) + (size_t)kRowWarps * dc * sizeof(int);
+        const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_ * (big ? 3 : 6), (items + kRowWarps - 1) / kRowWarps);
+        unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
+        if (big) {
+            if (!persist_attr_set_) {
+                CK(cudaFuncSetAttribute(row_pass_persist_kernel<T, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                persist_attr_set_ = true;
+            }
+            row_pass_persist_kernel<T, 72><<<pgrid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, gblock, jobs);
+        } else {
+            row_pass_persist_kernel<T, 32, false><<<pgrid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, gblock, jobs);
+        }
+    } else if (use_smem && reg_rows_ && max_row_deg_ == 72) {
         // the (.,72)-regular sum-product hot path: check messages staged in shared memory by TMA, 12 warps per SM
         const size_t smem = (size_t)kRowWarps * 72 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
         bool &attr_set = smem_attr_set_[sizeof(T) == 4];
@@ -212,6 +247,7 @@ int Engine::launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int 
     a.iters_out = out.iters; a.ok_out = out.is_codeword;
     a.M = M_; a.N = N_; a.g0 = 0; a.max_iter = max_iter; a.consider_new = consider_new; a.fixed_iters = fixed;
     a.counter = counter; a.finished = finished; a.counters_to_zero = rearm; a.clear_fresh = clear_fresh;
+    a.row_jobs = d_counters_ + (size_t)kRing * kCounterWords;
     const size_t smem = (size_t)N_ * sizeof(uint32_t);
     static const bool no_smem = getenv("DNALDPC_SYN_GATHER") != nullptr;  // A/B switch: global-gather variant
     if (!no_smem && smem <= (size_t)kSynSmemGate && N_ % 4 == 0) {  // the group's decision words staged in shared memory
