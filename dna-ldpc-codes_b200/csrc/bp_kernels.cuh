@@ -458,39 +458,63 @@ __device__ __forceinline__ void tmem_alloc_512(uint32_t *smem_slot) {  // one fu
 __device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {  // the allocating warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512u) : "memory");
 }
-// 8 doubles of this lane <-> 16 consecutive 32-bit columns of the lane's tensor-memory row
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const double (&d)[8]) {
+// One block of 8 edges of this lane <-> 18 consecutive 32-bit columns of the lane's tensor-memory row: the 8 factors d_k
+// and the backward product check-pointed at the top of the block.
+constexpr int kTmBlockCols = 18;
+__device__ __forceinline__ void tmem_st_block(uint32_t taddr, const double (&d)[8], double ck) {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[2 * i] = (uint32_t)__double2loint(d[i]); w[2 * i + 1] = (uint32_t)__double2hiint(d[i]); }
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  ::"r"(taddr), "r"(w[0]),"r"(w[1]),"r"(w[2]),"r"(w[3]),"r"(w[4]),"r"(w[5]),"r"(w[6]),"r"(w[7]),"r"(w[8]),"r"(w[9]),"r"(w[10]),"r"(w[11]),"r"(w[12]),"r"(w[13]),"r"(w[14]),"r"(w[15]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};"
+                 ::"r"(taddr + 16u), "r"((uint32_t)__double2loint(ck)), "r"((uint32_t)__double2hiint(ck)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, double (&d)[8]) {
-    uint32_t w[16];
+__device__ __forceinline__ void tmem_ld_block(uint32_t taddr, double (&d)[8], double &ck) {
+    uint32_t w[18];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(w[0]),"=r"(w[1]),"=r"(w[2]),"=r"(w[3]),"=r"(w[4]),"=r"(w[5]),"=r"(w[6]),"=r"(w[7]),"=r"(w[8]),"=r"(w[9]),"=r"(w[10]),"=r"(w[11]),"=r"(w[12]),"=r"(w[13]),"=r"(w[14]),"=r"(w[15]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(w[16]), "=r"(w[17]) : "r"(taddr + 16u) : "memory");
     // the registers are valid after the wait: tie them to it so that no use can be scheduled ahead of it
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(w[0]),"+r"(w[1]),"+r"(w[2]),"+r"(w[3]),"+r"(w[4]),"+r"(w[5]),"+r"(w[6]),"+r"(w[7]),"+r"(w[8]),"+r"(w[9]),"+r"(w[10]),"+r"(w[11]),"+r"(w[12]),"+r"(w[13]),"+r"(w[14]),"+r"(w[15]) :: "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(w[0]),"+r"(w[1]),"+r"(w[2]),"+r"(w[3]),"+r"(w[4]),"+r"(w[5]),"+r"(w[6]),"+r"(w[7]),"+r"(w[8]),"+r"(w[9]),"+r"(w[10]),"+r"(w[11]),"+r"(w[12]),"+r"(w[13]),"+r"(w[14]),"+r"(w[15]),"+r"(w[16]),"+r"(w[17]) :: "memory");
 #pragma unroll
     for (int i = 0; i < 8; i++) d[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+    ck = __hiloint2double((int)w[17], (int)w[16]);
+}
+
+// position of the r-th set bit of m for r < 8 (0 when m has fewer): 8 warp-uniform steps instead of __fns's search
+__device__ __forceinline__ int nth_set_bit8(uint32_t m, int r) {
+    int f = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (q == r && m) f = __ffs(m) - 1;
+        m &= m - 1;
+    }
+    return f;
 }
 
 constexpr int kTmWarps = 12;  // one CTA per SM: 12 tiles of shared memory, 3 warps per tensor-memory lane quarter
 
-// Persistent check pass, fp64, regular rows of degree DC (multiple of 8): jobs (check i, block of `gblock` groups) from
-// a device counter like row_pass_persist_kernel. Between pass 1 and pass 2 of an item the warp already starts its NEXT
-// item (the next group of the job, or the first group of the next job): the bulk copy into the freed tile and, when
-// lanes of that group start a frame, the first 8 ranks of their channel-ratio gather into registers that stay in
-// flight during pass 2.
+// Persistent check pass, fp64, regular rows of degree DC (multiple of 8). 12 resident warps per SM pull ITEMS (group g,
+// check i; consecutive items = consecutive checks of one group, so the channel-ratio lines that the lanes starting a
+// frame gather stay in L2 between the 8 checks that use a bit) from a device counter the syndrome kernel re-arms.
+// Software pipeline per warp, two items deep:
+//   top of item k    : claim item k+2 (atomic, result picked up at the end); slot masks and column indices of item k+1
+//                      requested into registers
+//   tile of k landed : the gathered ratios of the lanes that start a frame overwrite their columns
+//   pass 1 of k      : d_k and the check-pointed backward products to tensor memory (the shared-memory tile is free)
+//   start of k+1     : column indices to shared memory, bulk copy into the freed tile, gather of its starting lanes
+//                      into registers - all in flight during
+//   pass 2 of k      : factors back from tensor memory block by block, lr_k streamed to the message array.
+// Both passes are 9-trip loops over blocks of 8 edges (the whole kernel fits the instruction cache; the unrolled form
+// spent 15 % of its time waiting for instructions).
 template <int DC>
 __global__ void __launch_bounds__(kTmWarps * 32, 1)
 row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio, const uint32_t *__restrict__ actw,
                      const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
-                     int g0, int G, int gblock, unsigned int *__restrict__ job_counter, int l2_hint) {
-    static_assert(DC % 8 == 0 && 2 * DC * (kTmWarps / 4) <= 512, "tensor-memory columns");
-    constexpr int NB = DC / 8, NT = DC / 4;
-    const uint64_t policy = l2_evict_first_policy();
+                     int g0, int G, unsigned int *__restrict__ job_counter, int l2_hint) {
+    static_assert(DC % 8 == 0 && (DC / 8) * kTmBlockCols * (kTmWarps / 4) <= 512, "tensor-memory columns");
+    constexpr int NB = DC / 8, NT = DC / 4, NI = (DC + 31) / 32;
     constexpr uint32_t kTileBytes = DC * kFG * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -500,6 +524,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
     int *sidx = reinterpret_cast<int *>(aux + kTmWarps * sizeof(uint64_t)) + warp * DC;
     uint32_t *tm_slot = reinterpret_cast<uint32_t *>(aux + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * DC * sizeof(int));
     const double *col = tile + lane;
+    const uint64_t policy = l2_evict_first_policy();
     if (warp == 0) tmem_alloc_512(tm_slot);
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -510,27 +535,11 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm_base = *tm_slot;
     // this warp's rows: lane quarter (warp % 4) - the only one its tcgen05.ld / st can reach - and a private column range
-    const uint32_t taddr = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 2 * DC);
-    const int nblk = (G + gblock - 1) / gblock;
-    const unsigned njobs = (unsigned)M * (unsigned)nblk;
+    const uint32_t taddr = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * NB * kTmBlockCols);
+    const unsigned njobs = (unsigned)M * (unsigned)G;
     const int kq = lane >> 3, rk = lane & 7;
     uint32_t phase = 0;
 
-    // a job's first item: (check, first group); false when the counter has run out. Restages the column indices.
-    auto fetch_job = [&](int &g, int &gend, int &e0) -> bool {
-        unsigned job = 0;
-        if (lane == 0) job = atomicAdd(job_counter, 1u);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= njobs) return false;
-        const int jb = (int)(job / (unsigned)M), i = (int)(job - (unsigned)jb * (unsigned)M);
-        g = g0 + jb * gblock;
-        gend = min(g0 + G, g + gblock);
-        e0 = i * DC;
-        __syncwarp();  // nobody still reads the previous job's indices
-        for (int k = lane; k < DC; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
-        __syncwarp();
-        return true;
-    };
     // starts an item: bulk copy of its messages (if any lane carries on) and ranks 0..7 of the starting lanes' gather
     auto start_item = [&](int g, int e0, uint32_t act, uint32_t fw, double (&v)[NT]) {
         const uint32_t fresh_mask = fw & act;
@@ -542,28 +551,50 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
         }
         if (fresh_mask != 0) {
             const bool mine = rk < __popc(fresh_mask);
-            const int f = mine ? (int)__fns(fresh_mask, 0, rk + 1) : 0;
+            const int f = nth_set_bit8(fresh_mask, rk);
             const double *lr_base = lratio + (size_t)g * N * kFG;
 #pragma unroll
             for (int t = 0; t < NT; t++) v[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
         }
     };
+    auto claim_raw = [&]() -> unsigned {  // lane 0's register holds the item; nobody waits for it here
+        unsigned j = 0;
+        if (lane == 0) j = atomicAdd(job_counter, 1u);
+        return j;
+    };
 
-    int g = 0, gend = 0, e0 = 0;
-    bool valid = fetch_job(g, gend, e0);
+    unsigned job = __shfl_sync(0xffffffffu, claim_raw(), 0);
+    unsigned job_n = __shfl_sync(0xffffffffu, claim_raw(), 0);
+    int g = 0, e0 = 0;
     uint32_t act = 0, fw = 0;
     double v[NT];
-    if (valid) {
+    if (job < njobs) {  // the first item of this warp: nothing to overlap with yet
+        g = g0 + (int)(job / (unsigned)M);
+        e0 = (int)(job % (unsigned)M) * DC;
+        for (int k = lane; k < DC; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
+        __syncwarp();
         act = actw[g]; fw = freshw[g];
         if (act != 0) start_item(g, e0, act, fw, v);
     }
-    while (valid) {
+    while (job < njobs) {
+        // look ahead: claim the item after next; masks and column indices of the next item on their way
+        const unsigned raw_nn = claim_raw();
+        const bool valid_n = job_n < njobs;
+        const int g_n = g0 + (int)(job_n / (unsigned)M), e0_n = (int)(job_n % (unsigned)M) * DC;
         uint32_t act_n = 0, fw_n = 0;
-        if (g + 1 < gend) { act_n = actw[g + 1]; fw_n = freshw[g + 1]; }  // in flight during pass 1
+        int idx_n[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) idx_n[q] = 0;
+        if (valid_n) {
+            act_n = actw[g_n]; fw_n = freshw[g_n];
+#pragma unroll
+            for (int q = 0; q < NI; q++)
+                if (lane + 32 * q < DC) idx_n[q] = __ldg(col_idx + e0_n + lane + 32 * q);
+        }
         const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
         double *base = msg + ((size_t)g * E + e0) * kFG + lane;
-        const int e0_cur = e0, g_cur = g;
-        double ck[NB];
+        const double *lr_lane = lratio + (size_t)g * N * kFG + lane;
+        const int32_t *cols_cur = col_idx + e0;
         bool bad = false;
         if (act != 0) {
             const uint32_t fresh_mask = fw & act;
@@ -573,10 +604,9 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
             }
             if (fresh_mask != 0) {  // the gathered ratios overwrite the starting lanes' columns of the landed tile
                 const int nf = __popc(fresh_mask);
-                const double *lr_base = lratio + (size_t)g * N * kFG;
                 {
                     const bool mine = rk < nf;
-                    const int f = mine ? (int)__fns(fresh_mask, 0, rk + 1) : 0;
+                    const int f = nth_set_bit8(fresh_mask, rk);
 #pragma unroll
                     for (int t = 0; t < NT; t++)
                         if (mine) tile[(t * 4 + kq) * kFG + f] = v[t];
@@ -587,48 +617,46 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                     const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
                     double w[NT];
 #pragma unroll
-                    for (int t = 0; t < NT; t++) w[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
+                    for (int t = 0; t < NT; t++) w[t] = mine ? lr_lane[(size_t)sidx[t * 4 + kq] * kFG + (f - lane)] : 0.0;
 #pragma unroll
                     for (int t = 0; t < NT; t++)
                         if (mine) tile[(t * 4 + kq) * kFG + f] = w[t];
                 }
                 __syncwarp();
             }
-            // pass 1, descending: d_k to tensor memory, backward products check-pointed every 8 edges
+            // pass 1, descending: d_k and the check-pointed backward products to tensor memory
             double B = 1.0;
-#pragma unroll
+#pragma unroll 1
             for (int b = NB - 1; b >= 0; b--) {
                 double d8[8];
+                const double ckb = B;
 #pragma unroll
                 for (int kk = 7; kk >= 0; kk--) {
                     const double dk = check_factor(col[(b * 8 + kk) * kFG], bad);
                     d8[kk] = dk;
-                    if (kk == 7) ck[b] = B;
                     B = mul_rn(B, dk);
                 }
-                tmem_st8(taddr + (uint32_t)(b * 16), d8);
+                tmem_st_block(taddr + (uint32_t)(b * kTmBlockCols), d8, ckb);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            __syncwarp();  // every lane has read its column: the tile can take the next check
         }
-        // the successor: next group of this job, or the first group of the next job
-        if (g + 1 < gend) { g++; act = act_n; fw = fw_n; }
-        else {
-            valid = fetch_job(g, gend, e0);
-            if (valid) { act = actw[g]; fw = freshw[g]; }
-        }
-        if (valid && act != 0) start_item(g, e0, act, fw, v);
-        // (only `on`, `fresh`, `base`, `bad`, `ck`, `g_cur`, `e0_cur` still belong to the current item from here on)
-        if (on && bad) row_slow_path<double>(base, lratio + (size_t)g_cur * N * kFG + lane, col_idx + e0_cur, DC, fresh);  // invalid ratios: full IEEE divisions
+        __syncwarp();  // every lane has read its column and the staged indices: the tile and sidx can take the next item
+        // start of the next item
+#pragma unroll
+        for (int q = 0; q < NI; q++)
+            if (lane + 32 * q < DC) sidx[lane + 32 * q] = idx_n[q];
+        __syncwarp();
+        if (valid_n && act_n != 0) start_item(g_n, e0_n, act_n, fw_n, v);
+        // (only `on`, `fresh`, `base`, `lr_lane`, `cols_cur`, `bad` still belong to the current item from here on)
+        if (on && bad) row_slow_path<double>(base, lr_lane, cols_cur, DC, fresh);  // invalid ratios: full IEEE divisions
         // pass 2, ascending: factors back from tensor memory, lr_k streamed to the message array
-        if (__any_sync(0xffffffffu, on)) {
+        if (act != 0) {
             double F = 1.0;
             const bool store = on && !bad;
-#pragma unroll
+#pragma unroll 1
             for (int b = 0; b < NB; b++) {
                 double d8[8], Bv[8];
-                tmem_ld8(taddr + (uint32_t)(b * 16), d8);
-                Bv[7] = ck[b];
+                tmem_ld_block(taddr + (uint32_t)(b * kTmBlockCols), d8, Bv[7]);
 #pragma unroll
                 for (int kk = 7; kk > 0; kk--) Bv[kk - 1] = mul_rn(Bv[kk], d8[kk]);
 #pragma unroll
@@ -640,6 +668,8 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                 }
             }
         }
+        job = job_n; g = g_n; e0 = e0_n; act = act_n; fw = fw_n;
+        job_n = __shfl_sync(0xffffffffu, raw_nn, 0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -158,11 +158,9 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     static const bool no_persist = getenv("DNALDPC_ROW_PERSIST") == nullptr;  // A/B switch: persistent form (measured: no gain)
     static const int gblock = getenv("DNALDPC_ROW_GBLOCK") ? std::max(1, atoi(getenv("DNALDPC_ROW_GBLOCK"))) : 8;
     // Tensor memory as the second on-chip tile (row_pass_tmem_kernel): the default for the (.,72)-regular fp64 code.
-    // A/B switches: DNALDPC_ROW_NO_TMEM=1 -> the one-item-per-warp shared-memory kernel; job size and L2 policy of the
-    // bulk copies (measured: one group per job keeps the gathered channel-ratio lines of a group in L2 between the 8
-    // checks that use a bit, 1.81 ms per refill-regime launch against 1.88 / 2.15 ms with 4 / 8 groups per job).
+    // A/B switches: DNALDPC_ROW_NO_TMEM=1 -> the one-item-per-warp shared-memory kernel; DNALDPC_ROW_L2HINT=0 -> bulk
+    // copies without the evict-first policy.
     static const bool use_tmem = getenv("DNALDPC_ROW_NO_TMEM") == nullptr;
-    static const int tm_gblock = getenv("DNALDPC_ROW_GBLOCK") ? gblock : 1;
     static const int tm_hint = getenv("DNALDPC_ROW_L2HINT") ? atoi(getenv("DNALDPC_ROW_L2HINT")) : 1;
     if (use_smem && use_tmem && reg_rows_ && max_row_deg_ == 72) {
         // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
@@ -173,7 +171,7 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         }
         const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
         unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-        row_pass_tmem_kernel<72><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, std::min(tm_gblock, G), jobs, tm_hint);
+        row_pass_tmem_kernel<72><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
     } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
         // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
         const bool big = reg_rows_ && max_row_deg_ == 72;
