@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdnaldpc.so")
+LIB_PATH = os.environ.get("DNALDPC_LIB") or os.path.join(_HERE, "libdnaldpc.so")  # the override is for A/B runs of library builds
 
 OK = 0
 PREC_F64, PREC_F32 = 0, 1

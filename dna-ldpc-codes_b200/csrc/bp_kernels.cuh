@@ -506,9 +506,9 @@ constexpr int kTmWarps = 12;  // one CTA per SM: 12 tiles of shared memory, 3 wa
 //   start of k+1     : column indices to shared memory, bulk copy into the freed tile, gather of its starting lanes
 //                      into registers - all in flight during
 //   pass 2 of k      : factors back from tensor memory block by block, lr_k streamed to the message array.
-// Both passes are 9-trip loops over blocks of 8 edges (the whole kernel fits the instruction cache; the unrolled form
-// spent 15 % of its time waiting for instructions).
-template <int DC>
+// Both passes are loops over blocks of 8 edges, unrolled UR times (fully unrolled the kernel outgrows the instruction
+// cache and spends 15 % of a refill-regime launch waiting for instructions).
+template <int DC, int UR>
 __global__ void __launch_bounds__(kTmWarps * 32, 1)
 row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio, const uint32_t *__restrict__ actw,
                      const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
@@ -626,7 +626,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
             }
             // pass 1, descending: d_k and the check-pointed backward products to tensor memory
             double B = 1.0;
-#pragma unroll 1
+#pragma unroll(UR)
             for (int b = NB - 1; b >= 0; b--) {
                 double d8[8];
                 const double ckb = B;
@@ -653,7 +653,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
         if (act != 0) {
             double F = 1.0;
             const bool store = on && !bad;
-#pragma unroll 1
+#pragma unroll(UR)
             for (int b = 0; b < NB; b++) {
                 double d8[8], Bv[8];
                 tmem_ld_block(taddr + (uint32_t)(b * kTmBlockCols), d8, Bv[7]);
@@ -669,7 +669,8 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
             }
         }
         job = job_n; g = g_n; e0 = e0_n; act = act_n; fw = fw_n;
-        job_n = __shfl_sync(0xffffffffu, raw_nn, 0);
+        // pick up the claim made at the top (volatile: keeps its place behind pass 2, so the atomic's latency stays hidden)
+        asm volatile("shfl.sync.idx.b32 %0, %1, 0, 31, 0xffffffff;" : "=r"(job_n) : "r"(raw_nn));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -165,13 +165,25 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     if (use_smem && use_tmem && reg_rows_ && max_row_deg_ == 72) {
         // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
         const size_t smem = (size_t)kTmWarps * 72 * kFG * sizeof(double) + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * 72 * sizeof(int) + 16;
+        // Blocks of 8 edges per loop trip. Same-box A/B (1.53 GHz under the power cap; steady-state step / refill-regime
+        // launch): 9 (fully unrolled) 0.2387 Gbit/s / 1.86 ms, 3: 0.2367 / 1.69 ms, 1: 0.2345 / 1.73 ms - the unrolled
+        // form wins while every warp runs the same streaming code and loses once the warps spread over the gather /
+        // fix-up paths of groups that admit frames (instruction-cache misses), so the host picks per tick.
+        static const int ur_env = getenv("DNALDPC_ROW_UNROLL") ? atoi(getenv("DNALDPC_ROW_UNROLL")) : 0;
+        const int ur = ur_env ? ur_env : (steady_ ? 9 : 3);
         if (!tmem_attr_set_) {
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             tmem_attr_set_ = true;
         }
         const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
         unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-        row_pass_tmem_kernel<72><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
+#define TMROW(U) row_pass_tmem_kernel<72, U><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
+        if (ur == 9) TMROW(9);
+        else if (ur == 3) TMROW(3);
+        else TMROW(1);
+#undef TMROW
     } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
         // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
         const bool big = reg_rows_ && max_row_deg_ == 72;
