@@ -164,3 +164,95 @@ def test_cli_argument_variants_side_by_side(tmp_path, args):
         assert len(res) == 1
         outs[who] = (r.stdout, open(os.path.join(d, "dec_cw.txt"), "rb").read(), res[0], _strip_times(open(os.path.join(d, res[0])).read()))
     assert outs["ours"] == outs["ref"]
+
+
+def test_resident_worker_serves_the_unmodified_command_line(tmp_path):
+    """`ldpc --serve` + the same binary as a thin client ($DNALDPC_SOCKET): the pipeline's serial one-process-per-codeword
+    loop (ex_decoder/def_func.py:47-51) runs unchanged, every call answered by the worker with the stdout, the files
+    and the exit code of a local run - also for the error cases and for two parity-check files in turn."""
+    import json
+    import time
+    tmp = str(tmp_path)
+    cws = ol.load_codewords()
+    shutil.copyfile(ol.PCHK_18432, os.path.join(tmp, "H.pchk"))
+    shutil.copyfile(os.path.join(ol.GOLDEN, "small_n120_m60.pchk"), os.path.join(tmp, "S.pchk"))
+    names = []
+    for f in range(6):
+        eps = 0.006
+        llr = np.where((cws[f] ^ ol.bsc_flips(7, f, 18432, eps)) == 0, 1.0, -1.0) * np.log((1 - eps) / eps)
+        names.append(_write_inputs(tmp, f, llr, cws))
+    rs = np.random.RandomState(5)
+    with open(os.path.join(tmp, "cw_s.txt"), "w") as fh:
+        fh.write("0 " * 120)
+    with open(os.path.join(tmp, "soft_s.txt"), "w") as fh:
+        fh.write("\n".join(str(float(x)) for x in rs.randn(120) + 2.0))
+    sock = os.path.join(tmp, "w.sock")
+    env = dict(os.environ, DNALDPC_SOCKET=sock)
+    calls = [[LDPC, "0", "0", "0", "7", "200", "1", cw, sn, "H", "0", "0", "0", "0"] for cw, sn in names]
+    calls.append([LDPC, "0", "0", "0", "7", "50", "1", "cw_s", "soft_s", "S", "0", "0", "0", "0"])
+    calls.append([LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "nope", "0", "0", "0", "0"])          # unreadable pchk
+    calls.append([LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "H", "0", "0", "0"])                  # argc error
+    calls.append([LDPC, "0", "0", "0", "7", "200", "1", names[0][0], names[0][1], "H", "0", "0", "0", "0", "--timing"])
+    local = []
+    for c in calls:
+        r = subprocess.run(c, cwd=tmp, capture_output=True)
+        decs = {n: open(os.path.join(tmp, n), "rb").read() for n in sorted(os.listdir(tmp)) if n.startswith("dec_")}
+        local.append((r.returncode, r.stdout, decs))
+        for n in decs:
+            os.unlink(os.path.join(tmp, n))
+    worker = subprocess.Popen([LDPC, "--serve"], cwd="/", env=env, stderr=subprocess.PIPE)
+    try:
+        for _ in range(100):
+            if os.path.exists(sock):
+                break
+            time.sleep(0.05)
+        t_first = None
+        for k, c in enumerate(calls):
+            t0 = time.perf_counter()
+            r = subprocess.run(c, cwd=tmp, capture_output=True, env=env)
+            dt = time.perf_counter() - t0
+            if k == 0:
+                t_first = dt
+            decs = {n: open(os.path.join(tmp, n), "rb").read() for n in sorted(os.listdir(tmp)) if n.startswith("dec_")}
+            assert (r.returncode, r.stdout, decs) == local[k], (k, r.stderr)
+            for n in decs:
+                os.unlink(os.path.join(tmp, n))
+            if k in (1, 2, 3, 4, 5):
+                assert dt < 0.5 * max(t_first, 0.4), (k, dt, t_first)  # no CUDA context creation after the first call
+        tj = json.loads(r.stderr.decode().strip().splitlines()[-1])
+        assert tj["frames"] == 1 and len(tj["iterations"]) == 1 and tj["iterations"][0] == tj["total_iterations"]
+        assert tj["gpu_init_ms"] == 0.0  # the decoder came from the worker's cache
+    finally:
+        subprocess.run([LDPC, "--shutdown"], env=env, capture_output=True)
+        worker.wait(timeout=30)
+    assert not os.path.exists(sock)
+
+
+def test_cli_multi_gpu_list(tmp_path):
+    """--gpus N: the frames of a --list batch decoded on every visible GPU by the library's own dispatcher; same dec files
+    and stdout as on one GPU, per-frame iteration counts in the --timing line."""
+    import json
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least 2 GPUs")
+    tmp = str(tmp_path)
+    cws = ol.load_codewords()
+    shutil.copyfile(ol.PCHK_18432, os.path.join(tmp, "H.pchk"))
+    names = []
+    for f in range(96):
+        eps = [0.004, 0.006, 0.0075][f % 3]
+        llr = np.where((cws[f] ^ ol.bsc_flips(9, f, 18432, eps)) == 0, 1.0, -1.0) * np.log((1 - eps) / eps)
+        names.append(_write_inputs(tmp, f, llr, cws))
+    with open(os.path.join(tmp, "frames.lst"), "w") as fh:
+        fh.write("".join("%s %s\n" % n for n in names))
+    outs = []
+    for g in (1, nd):
+        r = subprocess.run([LDPC, "0", "0", "0", "7", "60", "1", "x", "x", "H", "0", "0", "0", "0", "--list", "frames.lst", "--timing",
+                            "--gpus", str(g)], cwd=tmp, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        tj = json.loads(r.stderr.decode().strip().splitlines()[-1])
+        decs = [open(os.path.join(tmp, "dec_%s.txt" % cw), "rb").read() for cw, _ in names]
+        outs.append((r.stdout, decs, tj["iterations"], tj["avg_iterations"]))
+        assert tj["gpus"] == g and len(tj["iterations"]) == 96
+    assert outs[0] == outs[1]
