@@ -6,6 +6,9 @@ refill, drain-tail compaction, kernel-variant choices) far beyond the test suite
 
   fuzz_gpu_vs_oracle.py SECONDS        flooding sum-product + min-sum, small code
   fuzz_gpu_vs_oracle.py SECONDS sw     sliding-window BP on the SC-LDPC code (window 1..14, code_type 0 / 1)
+  fuzz_gpu_vs_oracle.py SECONDS big    the n=18432 code (tensor-memory check pass, compact gathers of starting lanes): random
+                                       batch sizes / slot counts / iteration caps / eps mixes, host and device buffers,
+                                       a random sample of every batch (stragglers included) against the oracle
 """
 import os
 import sys
@@ -51,10 +54,61 @@ def main_sw(seconds):
     print("GPU sliding window vs oracle: %d batches, %d frames identical" % (batches, frames))
 
 
+def main_big(seconds):
+    import torch
+    ldpc = _pkg.load()
+    code, orc = ldpc.Code(ol.PCHK_18432), ol.Oracle(ol.PCHK_18432)
+    cws = ol.load_codewords()
+    N, W = 18432, 576
+    rs = np.random.RandomState(2024)
+    decs = {}
+    t0, frames, checked, batches = time.time(), 0, 0, 0
+    while time.time() - t0 < seconds:
+        wave = int(rs.choice([64, 256, 1024, 4096]))
+        F = int(rs.choice([40, 333, 1500, 6000]))
+        mi = int(rs.choice([3, 8, 20, 50]))
+        mix = [(0.004, 0.006), (0.006, 0.0075, 0.02), (0.0075,), (0.003, 0.02)][int(rs.randint(0, 4))]
+        seed = int(rs.randint(1, 1 << 30))
+        dec = decs.get(wave) or decs.setdefault(wave, ldpc.Decoder(code, wave_frames=wave))
+        eps = np.array([mix[f % len(mix)] for f in range(F)])
+        recv = np.stack([cws[f % 272] ^ ol.bsc_flips(seed, f, N, eps[f]) for f in range(F)])
+        lr = np.where(recv == 0, ((1 - eps) / eps)[:, None], (eps / (1 - eps))[:, None])
+        if rs.randint(0, 2):
+            r = dec.decode(ldpc.IN_LR_F64, lr, mi, want=("bits", "iters", "ok", "post"))
+            it, ok, bits, post = r["iters"], r["ok"], r["bits"], r["post"]
+        else:
+            d_lr = torch.from_numpy(lr).cuda()
+            d_bits = torch.zeros((F, W), dtype=torch.int32, device="cuda")
+            d_it = torch.zeros(F, dtype=torch.int32, device="cuda")
+            d_ok = torch.zeros(F, dtype=torch.uint8, device="cuda")
+            d_post = torch.zeros((F, N), dtype=torch.float64, device="cuda")
+            dec.decode_device(ldpc.IN_LR_F64, d_lr.data_ptr(), F, mi, bits_ptr=d_bits.data_ptr(), iters_ptr=d_it.data_ptr(),
+                              ok_ptr=d_ok.data_ptr(), post_ptr=d_post.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            it, ok, post = d_it.cpu().numpy(), d_ok.cpu().numpy(), d_post.cpu().numpy()
+            bits = np.unpackbits(d_bits.cpu().numpy().view(np.uint8).reshape(F, W * 4), axis=1, bitorder="little")[:, :N].astype(np.int8)
+        assert dec.stats()["frames"] == F and dec.stats()["frame_iters"] == int(it.sum())
+        sample = set(rs.choice(F, size=min(F, 6), replace=False).tolist())
+        sample |= set(np.nonzero(it == it.max())[0][:2].tolist()) | set(np.nonzero(it == it.min())[0][:1].tolist())
+        for f in sorted(sample):
+            o = orc.decode(lr[f], mi)
+            assert it[f] == o["n"] and ok[f] == o["ok"] and np.array_equal(bits[f], o["dblk"]), (wave, F, mi, mix, seed, f)
+            assert np.array_equal(post[f].view(np.uint64), o["post"].view(np.uint64)), ("post", wave, F, mi, mix, seed, f)
+        good = ok == 1
+        assert np.array_equal(bits[good], cws[np.arange(F)[good] % 272])  # every frame flagged as a codeword is the sent one
+        frames += F
+        checked += len(sample)
+        batches += 1
+    print("GPU n=18432 vs oracle: %d batches, %d frames (all flagged codewords = the sent ones), %d frames bit for bit incl. posteriors"
+          % (batches, frames, checked))
+
+
 def main():
     seconds = float(sys.argv[1])
     if len(sys.argv) > 2 and sys.argv[2] == "sw":
         return main_sw(seconds)
+    if len(sys.argv) > 2 and sys.argv[2] == "big":
+        return main_big(seconds)
     ldpc = _pkg.load()
     path = os.path.join(ol.GOLDEN, "small_n120_m60.pchk")
     code, orc = ldpc.Code(path), ol.Oracle(path)
