@@ -24,6 +24,13 @@ struct dnaldpc_decoder {
     dnaldpc_stats stats{};
 };
 
+// Every entry point leaves the calling thread's current CUDA device as it found it (the engines switch devices).
+struct DeviceRestore {
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 static thread_local std::string g_err;
 static int set_err(int rc, const std::string &m) {
     g_err = m;
@@ -103,6 +110,7 @@ int dnaldpc_code_check_regular(const dnaldpc_code *c, int *dv, int *regular_dv, 
 }
 
 int dnaldpc_decoder_create(const dnaldpc_code *c, const dnaldpc_config *cfg, dnaldpc_decoder **out) {
+    DeviceRestore restore_device;
     if (!c || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
     dnaldpc_config k{};
     if (cfg) k = *cfg;
@@ -137,7 +145,10 @@ int dnaldpc_decoder_create(const dnaldpc_code *c, const dnaldpc_config *cfg, dna
     return DNALDPC_OK;
 }
 
-void dnaldpc_decoder_destroy(dnaldpc_decoder *d) { delete d; }
+void dnaldpc_decoder_destroy(dnaldpc_decoder *d) {
+    DeviceRestore restore_device;
+    delete d;
+}
 
 static int check_input(const dnaldpc_input *in, int N) {
     if (!in) return set_err(DNALDPC_ERR_ARG, "null input descriptor");
@@ -152,6 +163,7 @@ static int check_input(const dnaldpc_input *in, int N) {
 }
 
 int dnaldpc_decode_batch(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter, const dnaldpc_output *out) {
+    DeviceRestore restore_device;
     if (!d || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
     int rc = check_input(in, d->c.N);
     if (rc) return rc;
@@ -164,6 +176,7 @@ int dnaldpc_decode_batch(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F,
 
 int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter,
                                 const dnaldpc_output *out, void *stream) {
+    DeviceRestore restore_device;
     if (!d || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
     int rc = check_input(in, d->c.N);
     if (rc) return rc;
@@ -177,6 +190,7 @@ int dnaldpc_decode_batch_device(dnaldpc_decoder *d, const dnaldpc_input *in, int
 
 int dnaldpc_decode_window(dnaldpc_decoder *d, const dnaldpc_window *win, const double *lratio, int64_t F, int max_iter,
                           const dnaldpc_output *out) {
+    DeviceRestore restore_device;
     if (!d || !win || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
     const int rc = d->eng[0]->decode_window_host(d->c, *win, lratio, F, max_iter, *out);
     if (rc) return set_err(rc, d->eng[0]->error());
@@ -266,6 +280,7 @@ static int sweep_host_exp(dnaldpc_decoder *d, const dnaldpc_input &in0, int64_t 
 
 int dnaldpc_redecode_sweep_ex(dnaldpc_decoder *d, const dnaldpc_input *in, int64_t F, int max_iter, const double *params,
                               int n_params, const dnaldpc_output *out, int32_t *rounds) {
+    DeviceRestore restore_device;
     if (!d || !in || !out || !params || n_params <= 0 || F < 0 || max_iter < 0) return set_err(DNALDPC_ERR_ARG, "bad argument");
     if (F > 0 && !in->data) return set_err(DNALDPC_ERR_ARG, "null input buffer");
     if (in->kind == DNALDPC_IN_LR_F64) return set_err(DNALDPC_ERR_ARG, "a sweep needs a parameter to vary: LR_F64 inputs have none");
@@ -314,6 +329,7 @@ int dnaldpc_bsc_table(double p, double *t) {  // channel.cpp:75-84
 
 int dnaldpc_synth_bsc_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
                              int64_t F, double eps, uint32_t *out_bits, void *stream) {
+    DeviceRestore restore_device;
     if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
     int rc = d->eng[0]->synth_bsc(cw_bits, n_cw, seed, frame0, F, eps, out_bits, (cudaStream_t)stream);
     return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
@@ -321,6 +337,7 @@ int dnaldpc_synth_bsc_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_
 
 int dnaldpc_synth_awgn_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
                               int64_t F, double sigma, float *out_y, void *stream) {
+    DeviceRestore restore_device;
     if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
     int rc = d->eng[0]->synth_awgn(cw_bits, n_cw, seed, frame0, F, sigma, out_y, (cudaStream_t)stream);
     return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
@@ -328,6 +345,7 @@ int dnaldpc_synth_awgn_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n
 
 int dnaldpc_synth_vote_device(dnaldpc_decoder *d, const uint32_t *cw_bits, int n_cw, uint64_t seed, int64_t frame0,
                               int64_t F, double mean_reads, double read_err, int8_t *out_k, void *stream) {
+    DeviceRestore restore_device;
     if (!d) return set_err(DNALDPC_ERR_ARG, "null decoder");
     int rc = d->eng[0]->synth_vote(cw_bits, n_cw, seed, frame0, F, mean_reads, read_err, out_k, (cudaStream_t)stream);
     return rc ? set_err(rc, d->eng[0]->error()) : DNALDPC_OK;
@@ -346,6 +364,7 @@ int dnaldpc_set_profiling(dnaldpc_decoder *d, int on) {
 }
 
 int dnaldpc_get_trace(dnaldpc_decoder *d, double *row_ms, double *col_ms, double *sched_ms, int *ticks) {
+    DeviceRestore restore_device;
     if (!d || !row_ms || !col_ms || !sched_ms) return set_err(DNALDPC_ERR_ARG, "null argument");
     const int n = d->eng[0]->trace_result(row_ms, col_ms, sched_ms);
     if (ticks) *ticks = n;
