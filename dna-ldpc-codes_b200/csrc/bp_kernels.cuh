@@ -756,8 +756,12 @@ __device__ __forceinline__ bool col_finish(const ColIn<T, DV> &c, T *__restrict_
     return P <= T(1);
 }
 
-template <typename T, int DV, bool EXACT, int ALG>
-__global__ void __launch_bounds__(kColWarps * 32, DV <= 8 ? 4 : 1)
+// BITS = bits whose loads a thread has in flight before the first one's arithmetic and stores (the stores to the message
+// array keep the compiler from hoisting the next bit's loads by itself). One bit is enough for fp64 columns of weight 8
+// (8 x 256-byte requests per warp); fp32 messages (128-byte requests) and low-weight columns (3 edges per bit in the
+// n=65536 code) need several to keep enough bytes in flight.
+template <typename T, int DV, bool EXACT, int ALG, int BITS>
+__global__ void __launch_bounds__(kColWarps * 32, DV > 8 ? 1 : (BITS * DV * (int)sizeof(T) <= 64 ? 4 : (BITS * DV <= 16 ? 3 : 2)))
 col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__restrict__ decw,
                 const uint32_t *__restrict__ actw, T *__restrict__ post, const int32_t *__restrict__ col_ptr,
                 const int32_t *__restrict__ col_edge, int N, int E, int g0, int cols_per_warp) {
@@ -777,13 +781,13 @@ col_pass_kernel(T *__restrict__ msg, const T *__restrict__ lratio, uint32_t *__r
         }
     };
     int j = jbeg;
-    if (sizeof(T) == 4) {  // fp32: 128-byte requests -> two bits' loads in flight per thread
-        for (; j + 1 < jend; j += 2) {
-            ColIn<T, DV> a, b;
-            col_load<T, DV, EXACT>(a, gmsg, lratio, col_ptr, col_edge, N, g, j, lane, on);
-            col_load<T, DV, EXACT>(b, gmsg, lratio, col_ptr, col_edge, N, g, j + 1, lane, on);
-            put(j, col_finish<T, DV, EXACT, ALG>(a, gmsg, post, N, g, j, lane, on));
-            put(j + 1, col_finish<T, DV, EXACT, ALG>(b, gmsg, post, N, g, j + 1, lane, on));
+    if (BITS > 1) {
+        for (; j + BITS - 1 < jend; j += BITS) {
+            ColIn<T, DV> in[BITS];
+#pragma unroll
+            for (int b = 0; b < BITS; b++) col_load<T, DV, EXACT>(in[b], gmsg, lratio, col_ptr, col_edge, N, g, j + b, lane, on);
+#pragma unroll
+            for (int b = 0; b < BITS; b++) put(j + b, col_finish<T, DV, EXACT, ALG>(in[b], gmsg, post, N, g, j + b, lane, on));
         }
     }
     for (; j < jend; j++) {
@@ -937,7 +941,7 @@ __device__ __forceinline__ void syn_tail(const SchedArrays &s, const SynArgs &a,
         s_ticket = atomicAdd(s.arrive + g, 1u);
     }
     __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
+    if (s_ticket != gridDim.x * gridDim.z - 1) return;
     if (threadIdx.x < 32) {  // last CTA of the group: every partial OR is visible
         __threadfence();
         const uint32_t unsat = *((volatile uint32_t *)(s.unsatw + g));
@@ -1046,6 +1050,50 @@ syndrome_update_smem_kernel(const uint32_t *__restrict__ decw, SchedArrays s, Sy
         acc |= p;
     }
     syn_tail<kSynSmemThreads>(s, a, g, act, consider, acc);
+}
+
+// Variant 3 (N decision words do not fit in shared memory, N half-words do): blockIdx.z selects 16 of the group's 32
+// slots; the CTA stages those slots' bits of all N words (N x 2 bytes) and works like variant 2 on them. The words are
+// read twice per group, which is nothing next to one 32-byte L2 sector per 4-byte gather of variant 1 (the n=65536 code:
+// 6.3 MB per group and launch).
+__global__ void __launch_bounds__(kSynSmemThreads)
+syndrome_update_half_kernel(const uint32_t *__restrict__ decw, SchedArrays s, SynArgs a, const int32_t *__restrict__ row_ptr,
+                            const int32_t *__restrict__ col_idx) {
+    extern __shared__ __align__(16) uint16_t shw[];
+    const int g = a.g0 + blockIdx.y, M = a.M, N = a.N, half = blockIdx.z;
+    uint32_t act;
+    const uint32_t consider = syn_head(s, a, g, act);
+    if (consider == 0) return;
+    const uint32_t *dw = decw + (size_t)g * N;
+    const int sh = 16 * half;
+    const int n4 = N >> 2;  // N % 4 == 0 (checked by the host): 16-byte loads, 8-byte stores
+    for (int q = threadIdx.x; q < n4; q += kSynSmemThreads) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(dw) + q);
+        uint2 o;
+        o.x = ((w.x >> sh) & 0xffffu) | (((w.y >> sh) & 0xffffu) << 16);
+        o.y = ((w.z >> sh) & 0xffffu) | (((w.w >> sh) & 0xffffu) << 16);
+        reinterpret_cast<uint2 *>(shw)[q] = o;
+    }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const int rows_per_iter = kSynSmemThreads / 8;
+    const int per_cta = (M + gridDim.x - 1) / gridDim.x;
+    const int i_beg = blockIdx.x * per_cta, i_end = min(M, i_beg + per_cta);
+    uint32_t acc = 0;
+    for (int ib = i_beg; ib < i_end; ib += rows_per_iter) {  // warp-uniform trip count
+        const int i = ib + (threadIdx.x >> 3);
+        uint32_t p = 0;
+        if (i < i_end) {
+            const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
+#pragma unroll 4
+            for (int e = e0 + sub; e < e1; e += 8) p ^= shw[__ldg(col_idx + e)];
+        }
+        p ^= __shfl_xor_sync(0xffffffffu, p, 1);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 2);
+        p ^= __shfl_xor_sync(0xffffffffu, p, 4);
+        acc |= p;
+    }
+    syn_tail<kSynSmemThreads>(s, a, g, act, consider, acc << sh);
 }
 
 // ------------------------------------------------------------------------------------------------

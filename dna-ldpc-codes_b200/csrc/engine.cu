@@ -230,19 +230,32 @@ template <typename T> int Engine::launch_col(int g0, int G, bool want_post, cuda
     T *post = want_post ? (T *)d_post_ : nullptr;
     SchedArrays s;
     fill_sched(s);
-    const int cpw = 8;  // columns per warp
+    // bits a thread keeps in flight (A/B switch DNALDPC_COL_BITS): 1 for fp64 columns of weight 8, several for fp32
+    // messages and for low-weight columns
+    static const int bits_env = getenv("DNALDPC_COL_BITS") ? atoi(getenv("DNALDPC_COL_BITS")) : 0;
+    const int bits_def = (max_col_deg_ <= 4) ? 4 : (sizeof(T) == 4 ? 2 : 1);
+    const int bits = (bits_env >= 1 && bits_env <= 4) ? bits_env : bits_def;
+    const int cpw = bits == 3 ? 9 : 8;  // columns per warp
     dim3 grid((unsigned)((N_ + kColWarps * cpw - 1) / (kColWarps * cpw)), (unsigned)G);
-#define COL(DV, EX)                                                                                                                      \
+#define COLB(DV, EX, B)                                                                                                                  \
     do {                                                                                                                                 \
-        if (minsum_) col_pass_kernel<T, DV, EX, ALG_MINSUM><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw); \
-        else col_pass_kernel<T, DV, EX, ALG_BP><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw);         \
+        if (minsum_) col_pass_kernel<T, DV, EX, ALG_MINSUM, B><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw); \
+        else col_pass_kernel<T, DV, EX, ALG_BP, B><<<grid, kColWarps * 32, 0, st>>>(msg, lr, d_decw_, s.actw, post, d_col_ptr_, d_col_edge_, N_, E_, g0, cpw);         \
+    } while (0)
+#define COL(DV, EX)                          \
+    do {                                     \
+        if (bits == 4) COLB(DV, EX, 4);      \
+        else if (bits == 3) COLB(DV, EX, 3); \
+        else if (bits == 2) COLB(DV, EX, 2); \
+        else COLB(DV, EX, 1);                \
     } while (0)
     if (reg_cols_ && max_col_deg_ == 8) COL(8, true);
     else if (reg_cols_ && max_col_deg_ == 3) COL(3, true);
     else if (max_col_deg_ <= 4) COL(4, false);
     else if (max_col_deg_ <= 8) COL(8, false);
-    else COL(16, false);
+    else COLB(16, false, 1);
 #undef COL
+#undef COLB
     stats.kernel_launches++;
     CK(cudaGetLastError());
     return DNALDPC_OK;
@@ -268,6 +281,12 @@ int Engine::launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int 
             syn_attr_set_ = true;
         }
         syndrome_update_smem_kernel<<<dim3(kSynSmemSplit, (unsigned)G), kSynSmemThreads, smem, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
+    } else if (!no_smem && (size_t)N_ * sizeof(uint16_t) <= (size_t)kSynHalfGate && N_ % 4 == 0) {  // 16 slots' bits of every word staged
+        if (!syn_half_attr_set_) {
+            CK(cudaFuncSetAttribute(syndrome_update_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynHalfGate));
+            syn_half_attr_set_ = true;
+        }
+        syndrome_update_half_kernel<<<dim3(kSynSmemSplit, (unsigned)G, 2), kSynSmemThreads, (size_t)N_ * sizeof(uint16_t), st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
     } else {
         syndrome_update_kernel<<<dim3(kSynSplit, (unsigned)G), kSynThreads, 0, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
     }

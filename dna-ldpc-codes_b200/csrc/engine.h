@@ -95,7 +95,7 @@ class Engine {
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
-    bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false, persist_attr_set_ = false, tmem_attr_set_ = false;
+    bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false, persist_attr_set_ = false, tmem_attr_set_ = false, syn_half_attr_set_ = false;
     bool steady_ = false;  // last polled tick: all slots busy, no frame admitted
     bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
@@ -116,6 +116,7 @@ class Engine {
     static constexpr int kCompactNum = 15, kCompactDen = 16;
     // largest dynamic shared-memory size the smem-staged syndrome kernel is ever launched with (N * 4 bytes <= gate)
     static constexpr int kSynSmemGate = 96 * 1024;
+    static constexpr int kSynHalfGate = 200 * 1024;  // same for the half-word variant (N * 2 bytes, one CTA per SM)
     unsigned long long *d_next_ = nullptr;               // {next_frame, avail, iter_sum}
     int32_t *d_rows_ = nullptr;                          // frame queue: in_row[cap_rows_], out_row[cap_rows_]
     int64_t cap_rows_ = 0;
