@@ -647,6 +647,7 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
     uint32_t *runw = s.actw;
     int32_t *n_pos = s.slot_iter, *sum = s.harv_iter;
     unsigned *remaining = d_counters_;
+    long long sw_upd = 0;  // updates launched so far (ring index of the progress counters)
     double *pr = (double *)d_msg_, *lr = (double *)d_sw_lr_, *lrat = (double *)d_lratio_;
     const size_t wpf = (size_t)(N_ + 31) / 32;
     const int64_t S = (int64_t)G * kFG;
@@ -673,10 +674,17 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
                 sw_init_kernel<<<dim3((unsigned)((r[7] - r[6] + 7) / 8), (unsigned)Gw), 256, 0, st>>>(pr, lr, lrat, d_col_ptr_, d_col_edge_, N_, E_, r[6], r[7]);
                 stats.kernel_launches++;
             }
-            for (int it = 0; it <= max_iter; it++) {  // every position runs at least one update, at most max_iter + 1
+            // Every position runs at least one update, at most max_iter + 1. The host does not wait for an update's
+            // "frames still running" count: it polls the count of kLag updates ago (ring of counters + events, like
+            // the flooding scheduler), so the stream never drains; the updates launched after the last frame of the
+            // position has finished find every group's run mask empty and return at once.
+            bool done = false;
+            for (int it = 0; it <= max_iter && !done; it++) {
+                unsigned *rem = d_counters_ + (sw_upd % kRing);
                 if (r[3] > r[2]) {
                     const long long items = (long long)Gw * (r[3] - r[2]);
-                    sw_row_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(pr, lr, runw, d_row_ptr_, E_, r[2], r[3], Gw);
+                    if (max_row_deg_ <= 8) sw_row_reg_kernel<8><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(pr, lr, runw, d_row_ptr_, E_, r[2], r[3], Gw);
+                    else sw_row_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(pr, lr, runw, d_row_ptr_, E_, r[2], r[3], Gw);
                     stats.kernel_launches++;
                 }
                 if (r[1] > r[0]) {
@@ -684,13 +692,17 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
                         pr, lr, lrat, d_decw_, runw, d_col_ptr_, d_col_edge_, d_edge_row_, N_, E_, r[0], r[1], r[2], r[3]);
                     stats.kernel_launches++;
                 }
-                CK(cudaMemsetAsync(remaining, 0, sizeof(unsigned), st));
+                CK(cudaMemsetAsync(rem, 0, sizeof(unsigned), st));
                 sw_syn_kernel<<<Gw, 256, 0, st>>>(d_decw_, runw, n_pos, sum, d_row_ptr_, d_col_idx_, N_, M_, r[0], r[4], r[2], r[5],
-                                                  max_iter, remaining, 0, w.L, nf, 0, nullptr, nullptr, nullptr);
+                                                  max_iter, rem, 0, w.L, nf, 0, nullptr, nullptr, nullptr);
                 stats.kernel_launches++;
-                CK(cudaMemcpyAsync(h_counters_, remaining, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (h_counters_[0] == 0) break;
+                CK(cudaMemcpyAsync(h_counters_ + (sw_upd % kRing), rem, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(ev_[sw_upd % kRing], st));
+                if (it >= kLag) {
+                    CK(cudaEventSynchronize(ev_[(sw_upd - kLag) % kRing]));
+                    done = h_counters_[(sw_upd - kLag) % kRing] == 0;
+                }
+                sw_upd++;
             }
         }
         sw_syn_kernel<<<Gw, 256, 0, st>>>(d_decw_, runw, n_pos, sum, d_row_ptr_, d_col_idx_, N_, M_, 0, N_, 0, M_, max_iter, remaining, 1,

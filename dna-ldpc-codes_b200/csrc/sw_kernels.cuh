@@ -12,8 +12,10 @@
 //   * the frames of a wave walk through the window positions together: a frame that satisfies the bounded syndrome of
 //     position t early waits (its messages untouched) until the slowest frame of the wave has finished t. Frames are
 //     independent, so each frame's arithmetic - and hence its result - is exactly the reference's;
-//   * the arithmetic uses nvcc's full-range IEEE division (the check_*_slow helpers): this mode is about coverage,
-//     the hand-tuned in-range sequences stay with the hot flooding kernels.
+//   * checks of degree <= 8 (the (3,6) protograph codes) run through sw_row_reg_kernel: the row's messages in registers,
+//     all loads in flight at once, the in-range division sequences of bp_math.cuh (bit-identical to IEEE division on
+//     their ranges; anything else falls back, per lane, to the full-range loop); higher degrees use the generic
+//     sw_row_kernel with nvcc's full-range division.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -94,6 +96,56 @@ sw_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, const uint
         const double t = __dmul_rn(l[(size_t)e * kFG], dl);
         l[(size_t)e * kFG] = check_to_bit_slow(t);
         dl = __dmul_rn(dl, check_factor_slow(p[(size_t)e * kFG]));
+    }
+}
+
+// The same update with the row in registers (degree <= DC): forward products F_k and backward products B_k are the
+// reference's (same multiplications in the same order: F runs up the row, B down), t = F_k * B_k, lr_k = (1+t)/(1-t).
+template <int DC>
+__global__ void __launch_bounds__(128)
+sw_row_reg_kernel(const double *__restrict__ pr, double *__restrict__ lr, const uint32_t *__restrict__ runw,
+                  const int32_t *__restrict__ row_ptr, int E, int c0, int c1, int G) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int rows = c1 - c0;
+    if (item >= (long long)G * rows) return;
+    const int g = (int)(item / rows), i = c0 + (int)(item - (long long)g * rows);
+    if (!((runw[g] >> lane) & 1u)) return;
+    const int e0 = __ldg(row_ptr + i), deg = __ldg(row_ptr + i + 1) - e0;
+    const double *p = pr + ((size_t)g * E + e0) * kFG + lane;
+    double *l = lr + ((size_t)g * E + e0) * kFG + lane;
+    double d[DC], Bv[DC];
+#pragma unroll
+    for (int k = 0; k < DC; k++) d[k] = k < deg ? ld_stream(p + (size_t)k * kFG) : 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < DC; k++) d[k] = k < deg ? check_factor(d[k], bad) : 1.0;  // padding: exact identity in both chains
+    if (bad) {  // operands outside the proven ranges (negative / NaN ratios): the full-range loop of sw_row_kernel for this lane
+        double dl = 1.0;
+        for (int k = 0; k < deg; k++) {
+            l[(size_t)k * kFG] = dl;
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+        }
+        dl = 1.0;
+        for (int k = deg - 1; k >= 0; k--) {
+            const double t = __dmul_rn(l[(size_t)k * kFG], dl);
+            l[(size_t)k * kFG] = check_to_bit_slow(t);
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+        }
+        return;
+    }
+    double B = 1.0;
+#pragma unroll
+    for (int k = DC - 1; k >= 0; k--) {
+        Bv[k] = B;
+        B = __dmul_rn(B, d[k]);
+    }
+    double F = 1.0;
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        const double t = __dmul_rn(F, Bv[k]);
+        if (k < deg) st_stream(l + (size_t)k * kFG, check_to_bit(t));
+        F = __dmul_rn(F, d[k]);
     }
 }
 

@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Throughput of the sliding-window decoder (dnaldpc_decode_window = Run_SW_Decoder, dec.cpp:2092-2196) on a terminated
+(3,6) spatially-coupled code from tools/gen_sc_pchk.py (Z x L), BSC inputs, host buffers. Prints frames/s, window
+updates per frame and the algorithmic GB/s of the update kernels: per update of a position the check kernel reads pr and
+writes lr for every edge of the window's checks (16 B per edge) and the bit kernel reads lr and rewrites pr for every
+in-window edge of the window's bits (24 B per edge) plus the channel ratio (8 B per bit).
+  python tools/bench_sw.py [--z 1024] [--L 24] [--win 6] [--frames 8192] [--eps 0.03] [--max-iter 20]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import _pkg  # noqa: E402
+import gen_sc_pchk  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--z", type=int, default=1024)
+    ap.add_argument("--L", type=int, default=24)
+    ap.add_argument("--win", type=int, default=6)
+    ap.add_argument("--frames", type=int, default=8192)
+    ap.add_argument("--eps", type=float, default=0.03)
+    ap.add_argument("--max-iter", type=int, default=20)
+    ap.add_argument("--wave", type=int, default=4096)
+    a = ap.parse_args()
+    ldpc = _pkg.load()
+    M, N, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(a.z, a.L, 11)
+    code = ldpc.Code(csr=(M, N, row_ptr, col_idx))
+    dec = ldpc.Decoder(code, devices=[0], wave_frames=a.wave)
+    rs = np.random.RandomState(1)
+    flips = rs.rand(a.frames, N) < a.eps          # all-zero codeword through a BSC
+    lr = np.where(flips, a.eps / (1 - a.eps), (1 - a.eps) / a.eps)
+    D = a.L + 3 - 1
+    import torch
+    lr = torch.from_numpy(lr).pin_memory().numpy()  # pinned host buffer: the copies run at PCIe speed
+    dec.decode_window(lr[:a.wave], a.max_iter, a.L, 3, a.win, Mv[:D], Mc[:D])  # warm-up: slot arrays
+    t0 = time.perf_counter()
+    r = dec.decode_window(lr, a.max_iter, a.L, 3, a.win, Mv[:D], Mc[:D])
+    dt = time.perf_counter() - t0
+    st = dec.stats()
+    # updates per frame = L positions x (n + 1); iters = floor(sum n / L)
+    upd = float((r["iters"].astype(np.float64) + 1).sum()) * a.L
+    edges_win = a.win * 2 * a.z * 3               # edges of the bits of one full window
+    bytes_upd = 16.0 * (a.win + 2) * a.z * 6 + 24.0 * edges_win + 8.0 * a.win * 2 * a.z
+    out = {"code": {"Z": a.z, "L": a.L, "N": N, "M": M, "E": int(len(col_idx)), "win": a.win}, "frames": a.frames, "eps": a.eps,
+           "max_iter": a.max_iter, "seconds": dt, "frames_per_s": a.frames / dt, "decoded_gbit_s": a.frames * N / dt / 1e9,
+           "fer": 1.0 - float((r["ok"] == 1).mean()), "bit_errors": int(r["bits"].sum()),
+           "avg_updates_per_position": upd / a.frames / a.L, "kernel_launches": st["kernel_launches"],
+           "algorithmic_gb_s": upd * bytes_upd / dt / 1e9}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
