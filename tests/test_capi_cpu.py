@@ -115,3 +115,62 @@ def test_cli_argument_errors_without_gpu(tmp_path):
     assert r.returncode == 1 and "not supported" in r.stderr
     r = run("0", "0", "0", "7", "20", "1", "cw", "soft", "nosuch", "0", "0", "0", "0")
     assert r.returncode == 1 and "nosuch.pchk" in r.stderr
+
+
+def test_resident_worker_protocol_without_gpu(tmp_path):
+    """`ldpc --serve` and the client mode of the same binary: the command line, the working directory, stdout / stderr and
+    the exit code travel over the Unix socket (error paths only here: nothing reaches a GPU); without a worker the client
+    runs locally; --shutdown stops the worker and removes the socket."""
+    import subprocess
+    import time
+    LDPC = os.path.join(ROOT, "dna-ldpc-codes_b200", "ldpc")
+    tmp = str(tmp_path)
+    sock = os.path.join(tmp, "w.sock")
+    env = dict(os.environ, DNALDPC_SOCKET=sock)
+    bad_pchk = [LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "nope", "0", "0", "0", "0"]
+    bad_argc = [LDPC, "0", "0", "0", "7", "200", "1", "a", "b", "nope", "0", "0", "0"]
+    local = [subprocess.run(c, cwd=tmp, capture_output=True) for c in (bad_pchk, bad_argc)]
+    assert local[0].returncode == 1 and b"Can't open parity check file: nope.pchk" in local[0].stderr
+    assert local[1].returncode == 1 and b"argc error!" in local[1].stderr
+    # no worker yet: the client falls back to a local run, --shutdown reports that nobody answers
+    r = subprocess.run(bad_pchk, cwd=tmp, capture_output=True, env=env)
+    assert (r.returncode, r.stdout, r.stderr) == (local[0].returncode, local[0].stdout, local[0].stderr)
+    r = subprocess.run([LDPC, "--shutdown"], capture_output=True, env=env)
+    assert r.returncode == 1 and b"no worker answers" in r.stderr
+    worker = subprocess.Popen([LDPC, "--serve"], cwd="/", env=env, stderr=subprocess.PIPE)
+    try:
+        for _ in range(200):
+            if os.path.exists(sock):
+                break
+            time.sleep(0.02)
+        assert os.path.exists(sock)
+        for c, ref in zip((bad_pchk, bad_argc), local):
+            r = subprocess.run(c, cwd=tmp, capture_output=True, env=env)
+            assert (r.returncode, r.stdout, r.stderr) == (ref.returncode, ref.stdout, ref.stderr)
+    finally:
+        r = subprocess.run([LDPC, "--shutdown"], capture_output=True, env=env)
+        worker.wait(timeout=20)
+    assert r.returncode == 0 and worker.returncode == 0 and not os.path.exists(sock)
+
+
+def test_generator_twins_are_deterministic_and_plausible():
+    """Host twins of the device input generators (oracle/bp_oracle.c): keyed by (seed, frame, bit) only, Poisson reads and
+    Gaussian noise with the requested parameters, the codeword's sign applied."""
+    N = 18432
+    cw = (np.arange(N) % 3 == 0).astype(np.int8)
+    k1, k2 = ol.synth_vote(cw, 5, 77, N, 3.9, 0.01), ol.synth_vote(cw, 5, 77, N, 3.9, 0.01)
+    assert np.array_equal(k1, k2) and not np.array_equal(k1, ol.synth_vote(cw, 5, 78, N, 3.9, 0.01))
+    k0 = ol.synth_vote(None, 5, 77, N, 3.9, 0.01)
+    assert np.array_equal(k1, np.where(cw == 0, k0, -k0))
+    reads = np.abs(k0.astype(np.int32))                       # 1 % wrong reads: |k| is the read count almost always
+    assert abs(reads.mean() - 3.9 * 0.98) < 0.08 and (k0 >= 0).mean() > 0.97
+    y = ol.synth_awgn(cw, 9, 3, N, 0.5)
+    assert np.array_equal(y, ol.synth_awgn(cw, 9, 3, N, 0.5))
+    noise = y - np.where(cw == 0, 1.0, -1.0)
+    assert abs(noise.mean()) < 0.02 and abs(noise.std() - 0.5) < 0.02
+    # the noise is Box-Muller on rng streams 4 / 5 exactly as specified in include/dnaldpc.h
+    j = np.arange(8)
+    u1 = ((ol.rng_u64(9, 3, j, 4) >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
+    u2 = (ol.rng_u64(9, 3, j, 5) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    want = (np.where(cw[:8] == 0, 1.0, -1.0) + 0.5 * np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586476925286766559 * u2)).astype(np.float32)
+    assert np.allclose(y[:8], want, rtol=1e-6, atol=0)
