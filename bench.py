@@ -460,6 +460,7 @@ def run_ours(args):
     if os.path.exists(tr):
         try:
             roof["traffic"] = json.load(open(tr)).get("row_per_frame" if row_ms >= col_ms else "col_per_frame") * frames_per_launch
+            roof["traffic_source"] = "profiles/traffic.json: dram__bytes_read + dram__bytes_write of one ncu --set full capture of this kernel (profiles/r02/ncu_full_row_col.md), scaled to this launch; not re-measured in this run"
         except Exception:
             pass
 
