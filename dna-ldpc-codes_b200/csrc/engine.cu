@@ -154,7 +154,8 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     static const bool no_smem = getenv("DNALDPC_ROW_REGS") != nullptr;  // A/B switch: register-resident check kernel
     // A/B switch: the round-1 policy (smem-staged kernel only in ticks where every slot is busy and nobody is admitted)
     static const bool steady_only = getenv("DNALDPC_ROW_SMEM_STEADY_ONLY") != nullptr;
-    const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && sizeof(T) == 8;
+    static const bool f32_smem = getenv("DNALDPC_ROW_SMEM_F32") != nullptr;  // A/B switch: TMA-staged check pass for fp32 too
+    const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && (sizeof(T) == 8 || f32_smem);
     static const bool no_persist = getenv("DNALDPC_ROW_PERSIST") == nullptr;  // A/B switch: persistent form (measured: no gain)
     static const int gblock = getenv("DNALDPC_ROW_GBLOCK") ? std::max(1, atoi(getenv("DNALDPC_ROW_GBLOCK"))) : 8;
     // Tensor memory as the second on-chip tile (row_pass_tmem_kernel): the default for the (.,72)-regular fp64 code.
@@ -162,7 +163,7 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     // copies without the evict-first policy.
     static const bool use_tmem = getenv("DNALDPC_ROW_NO_TMEM") == nullptr;
     static const int tm_hint = getenv("DNALDPC_ROW_L2HINT") ? atoi(getenv("DNALDPC_ROW_L2HINT")) : 1;
-    if (use_smem && use_tmem && reg_rows_ && max_row_deg_ == 72) {
+    if (use_smem && use_tmem && sizeof(T) == 8 && reg_rows_ && max_row_deg_ == 72) {
         // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
         const size_t smem = (size_t)kTmWarps * 72 * kFG * sizeof(double) + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * 72 * sizeof(int) + 16;
         // Blocks of 8 edges per loop trip. Same-box A/B (1.53 GHz under the power cap; steady-state step / refill-regime
