@@ -508,7 +508,7 @@ constexpr int kTmWarps = 12;  // one CTA per SM: 12 tiles of shared memory, 3 wa
 //   pass 2 of k      : factors back from tensor memory block by block, lr_k streamed to the message array.
 // Both passes are loops over blocks of 8 edges, unrolled UR times (fully unrolled the kernel outgrows the instruction
 // cache and spends 15 % of a refill-regime launch waiting for instructions).
-template <int DC, int UR>
+template <int DC, int UR, bool R16>
 __global__ void __launch_bounds__(kTmWarps * 32, 1)
 row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio, const uint32_t *__restrict__ actw,
                      const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
@@ -541,7 +541,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
     uint32_t phase = 0;
 
     // starts an item: bulk copy of its messages (if any lane carries on) and ranks 0..7 of the starting lanes' gather
-    auto start_item = [&](int g, int e0, uint32_t act, uint32_t fw, double (&v)[NT]) {
+    auto start_item = [&](int g, int e0, uint32_t act, uint32_t fw, double (&v)[NT], double (&v2)[R16 ? NT : 1]) {
         const uint32_t fresh_mask = fw & act;
         if ((act & ~fresh_mask) != 0 && lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses to the tile before the bulk write
@@ -555,6 +555,12 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
             const double *lr_base = lratio + (size_t)g * N * kFG;
 #pragma unroll
             for (int t = 0; t < NT; t++) v[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
+            if (R16 && __popc(fresh_mask) > 8) {  // ranks 8..15 travel along as well (kinds with many starting lanes per tick)
+                const bool mine2 = rk + 8 < __popc(fresh_mask);
+                const int f2 = mine2 ? (int)__fns(fresh_mask, 0, rk + 9) : 0;
+#pragma unroll
+                for (int t = 0; t < (R16 ? NT : 1); t++) v2[t] = mine2 ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f2] : 0.0;
+            }
         }
     };
     auto claim_raw = [&]() -> unsigned {  // lane 0's register holds the item; nobody waits for it here
@@ -567,14 +573,14 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
     unsigned job_n = __shfl_sync(0xffffffffu, claim_raw(), 0);
     int g = 0, e0 = 0;
     uint32_t act = 0, fw = 0;
-    double v[NT];
+    double v[NT], v2[R16 ? NT : 1];
     if (job < njobs) {  // the first item of this warp: nothing to overlap with yet
         g = g0 + (int)(job / (unsigned)M);
         e0 = (int)(job % (unsigned)M) * DC;
         for (int k = lane; k < DC; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
         __syncwarp();
         act = actw[g]; fw = freshw[g];
-        if (act != 0) start_item(g, e0, act, fw, v);
+        if (act != 0) start_item(g, e0, act, fw, v, v2);
     }
     while (job < njobs) {
         // look ahead: claim the item after next; masks and column indices of the next item on their way
@@ -611,7 +617,14 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                     for (int t = 0; t < NT; t++)
                         if (mine) tile[(t * 4 + kq) * kFG + f] = v[t];
                 }
-                for (int r0 = 8; r0 < nf; r0 += 8) {  // more than 8 starting lanes (first ticks of a batch): further rounds, not overlapped
+                if (R16 && nf > 8) {
+                    const bool mine = rk + 8 < nf;
+                    const int f = mine ? (int)__fns(fresh_mask, 0, rk + 9) : 0;
+#pragma unroll
+                    for (int t = 0; t < (R16 ? NT : 1); t++)
+                        if (mine) tile[(t * 4 + kq) * kFG + f] = v2[t];
+                }
+                for (int r0 = R16 ? 16 : 8; r0 < nf; r0 += 8) {  // still more starting lanes (first ticks of a batch): further rounds, not overlapped
                     const int r = r0 + rk;
                     const bool mine = r < nf;
                     const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
@@ -646,7 +659,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
         for (int q = 0; q < NI; q++)
             if (lane + 32 * q < DC) sidx[lane + 32 * q] = idx_n[q];
         __syncwarp();
-        if (valid_n && act_n != 0) start_item(g_n, e0_n, act_n, fw_n, v);
+        if (valid_n && act_n != 0) start_item(g_n, e0_n, act_n, fw_n, v, v2);
         // (only `on`, `fresh`, `base`, `lr_lane`, `cols_cur`, `bad` still belong to the current item from here on)
         if (on && bad) row_slow_path<double>(base, lr_lane, cols_cur, DC, fresh);  // invalid ratios: full IEEE divisions
         // pass 2, ascending: factors back from tensor memory, lr_k streamed to the message array
@@ -1148,7 +1161,7 @@ constexpr int kHsTilesPerWarp = 2;  // tiles a warp walks through
 template <typename T, int KIND, int ALG>
 __global__ void __launch_bounds__(kHsWarps * 32)
 harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ lratio, const T *__restrict__ post,
-                     uint32_t *__restrict__ decw, int N, int g0) {
+                     uint32_t *__restrict__ decw, int N, int g0, int tiles_per_warp) {
     const int g = g0 + blockIdx.y;
     const uint32_t hv = s.harvw[g], nf = s.newfw[g];
     if ((hv | nf) == 0) return;
@@ -1161,8 +1174,8 @@ harvest_setup_kernel(SetupArgs a, HarvestArgs h, SchedArrays s, T *__restrict__ 
     const int my_old = is_old ? __ldcg(s.out_row + s.harv_frame[g * kFG + lane]) : 0;
     const int my_oldit = s.harv_iter[g * kFG + lane];
     const int ntiles = (N + 31) / 32;
-    const int t0 = (blockIdx.x * kHsWarps + warp) * kHsTilesPerWarp;
-    for (int tile_id = t0; tile_id < min(ntiles, t0 + kHsTilesPerWarp); tile_id++) {
+    const int t0 = (blockIdx.x * kHsWarps + warp) * tiles_per_warp;
+    for (int tile_id = t0; tile_id < min(ntiles, t0 + tiles_per_warp); tile_id++) {
         const int j0 = tile_id * 32;
         const int j = j0 + lane;                                              // lane = bit of the tile
         uint32_t word = (j < N) ? decw[(size_t)g * N + j] : 0u;               // decisions of bit j, one bit per slot

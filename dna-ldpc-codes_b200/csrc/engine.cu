@@ -173,17 +173,26 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         static const int ur_env = getenv("DNALDPC_ROW_UNROLL") ? atoi(getenv("DNALDPC_ROW_UNROLL")) : 0;
         const int ur = ur_env ? ur_env : (steady_ ? 9 : 3);
         if (!tmem_attr_set_) {
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             tmem_attr_set_ = true;
         }
         const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
         unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-#define TMROW(U) row_pass_tmem_kernel<72, U><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
-        if (ur == 9) TMROW(9);
-        else if (ur == 3) TMROW(3);
-        else TMROW(1);
+#define TMROW(U, R) row_pass_tmem_kernel<72, U, R><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
+        // A/B switch DNALDPC_ROW_R16=1: in ticks that admit more than a quarter of the slots (frames of 2-4 iterations:
+        // vote counts, AWGN at high SNR; more than 8 lanes of a group start per tick) use the variant that keeps 16 ranks
+        // of the gather in flight (it fits at one block per trip). Measured: 368 k vs 371 k vote-count frames/s, 232 k
+        // vs 233 k AWGN frames/s - the second gather round was not what those regimes wait for; off by default.
+        static const bool r16_on = getenv("DNALDPC_ROW_R16") != nullptr && atoi(getenv("DNALDPC_ROW_R16")) != 0;
+        const bool r16 = r16_on && many_fresh_;
+        if (r16 && !ur_env) TMROW(1, true);
+        else if (ur == 9) TMROW(9, false);
+        else if (ur == 3) TMROW(3, false);
+        else if (r16) TMROW(1, true);
+        else TMROW(1, false);
 #undef TMROW
     } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
         // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
@@ -281,7 +290,8 @@ int Engine::launch_syndrome(const dnaldpc_output &out, int G, int max_iter, int 
             CK(cudaFuncSetAttribute(syndrome_update_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemGate));
             syn_attr_set_ = true;
         }
-        syndrome_update_smem_kernel<<<dim3(kSynSmemSplit, (unsigned)G), kSynSmemThreads, smem, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
+        static const int split = getenv("DNALDPC_SYN_SPLIT") ? std::max(1, atoi(getenv("DNALDPC_SYN_SPLIT"))) : kSynSmemSplit;  // A/B switch
+        syndrome_update_smem_kernel<<<dim3((unsigned)split, (unsigned)G), kSynSmemThreads, smem, st>>>(d_decw_, s, a, d_row_ptr_, d_col_idx_);
     } else if (!no_smem && (size_t)N_ * sizeof(uint16_t) <= (size_t)kSynHalfGate && N_ % 4 == 0) {  // 16 slots' bits of every word staged
         if (!syn_half_attr_set_) {
             CK(cudaFuncSetAttribute(syndrome_update_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynHalfGate));
@@ -313,14 +323,15 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
         syndrome_bytes_kernel<<<grid, 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, M_, N_, g0, out.pchk);
         stats.kernel_launches++;
     }
-    constexpr int tiles_per_cta = kHsWarps * kHsTilesPerWarp;
+    static const int tpw = getenv("DNALDPC_HS_TILES") ? std::max(1, atoi(getenv("DNALDPC_HS_TILES"))) : kHsTilesPerWarp;  // A/B switch
+    const int tiles_per_cta = kHsWarps * tpw;
     dim3 grid((unsigned)(((N_ + 31) / 32 + tiles_per_cta - 1) / tiles_per_cta), (unsigned)G);
     T *lr = (T *)d_lratio_;
     const T *post = (const T *)d_post_;
 #define HS(K)                                                                                                   \
     do {                                                                                                        \
-        if (minsum_) harvest_setup_kernel<T, K, ALG_MINSUM><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0); \
-        else harvest_setup_kernel<T, K, ALG_BP><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0);         \
+        if (minsum_) harvest_setup_kernel<T, K, ALG_MINSUM><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0, tpw); \
+        else harvest_setup_kernel<T, K, ALG_BP><<<grid, kHsWarps * 32, 0, st>>>(a, h, s, lr, post, d_decw_, N_, g0, tpw);         \
     } while (0)
     switch (in.kind) {
         case DNALDPC_IN_LR_F64: HS(IN_LR_F64); break;
@@ -354,12 +365,13 @@ int Engine::set_device() {
     return DNALDPC_OK;
 }
 
+// Called from a source's producer thread while the tick thread is inside run(): touches neither err_ nor stats.
 int Engine::publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream) {
     if (n <= 0) return DNALDPC_OK;
     const int64_t q0 = published_.load(std::memory_order_relaxed);
-    if (q0 + n > cap_rows_) return fail("frame queue overflow (more frames published than the session announced)", DNALDPC_ERR_ARG);
+    if (q0 + n > cap_rows_) return DNALDPC_ERR_ARG;  // more frames published than the session announced
     publish_kernel<<<1, 1024, 0, stream>>>(d_rows_, d_rows_ + cap_rows_, (long long)q0, n, list_in, row0_in, row0_out, d_next_ + 1);
-    CK(cudaGetLastError());
+    if (cudaGetLastError() != cudaSuccess) return DNALDPC_ERR_CUDA;
     published_.store(q0 + n, std::memory_order_release);
     return DNALDPC_OK;
 }
@@ -412,6 +424,7 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
     // the queue is empty and *avail == 0 from here on in stream order; producers on other streams wait for this point
     CK(cudaEventRecord(ready_ev_, st));
     steady_ = false;
+    many_fresh_ = false;
     traced_ = 0;
 
     // One tick = admit/harvest/check (twice) + one check-node pass + one bit-node pass over all slots.
@@ -434,7 +447,7 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
     const int fixed = (in.flags & DNALDPC_FLAG_FIXED_ITERS) ? 1 : 0;
     for (long long tick = 0;; tick++) {
         rc = src.pump(*this, admitted_total, low_water, &final);
-        if (rc) return rc;
+        if (rc) return err_.empty() ? fail("the frame source of this batch failed", rc) : rc;
         const long long pub = published();
         // ring entry of this tick: [0] slots in use, [1] frames admitted, [2] frames finished, [3] low-water q
         unsigned *cnt = d_counters_ + kCounterWords * (tick % kRing);
@@ -475,6 +488,7 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
             if (final && admitted_total == published() && last_inuse == 0) break;  // drained: nothing active, unharvested or pending
             // steady state = every slot busy and nobody being admitted (e.g. long-running frames)
             steady_ = last_admitted == 0 && last_inuse >= (unsigned)S;
+            many_fresh_ = (long long)last_admitted * 4 > S;
             if (!final && last_inuse == 0 && admitted_total == published()) {
                 // Idle engine, starved source: do not spin empty ticks. The check / bit passes below still run: this tick's
                 // admission kernels are already queued and may pick up frames published meanwhile, and a slot's fresh mark

@@ -97,6 +97,7 @@ class Engine {
     bool reg_rows_ = false, reg_cols_ = false;
     bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false, persist_attr_set_ = false, tmem_attr_set_ = false, syn_half_attr_set_ = false;
     bool steady_ = false;  // last polled tick: all slots busy, no frame admitted
+    bool many_fresh_ = false;  // last polled tick: more than a quarter of the slots admitted a frame
     bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
     // H edge tables (device)

@@ -51,20 +51,26 @@ class HostSource : public FrameSource {
   public:
     // in_ring / out_ring: frames the device staging rings hold (multiples of the chunk size). keep = rows are never
     // reused (in_ring == out_ring == capacity): the inputs stay resident for later re-decoding rounds.
-    HostSource(Engine &e, HostBatch &b, int64_t in_ring, int64_t out_ring, bool keep)
-        : e_(e), b_(b), in_ring_(in_ring), out_ring_(out_ring), keep_(keep) {}
+    // min_out_ring: how far the output ring may shrink when the device cannot hold it (0 = as given).
+    HostSource(Engine &e, HostBatch &b, int64_t in_ring, int64_t out_ring, bool keep, int64_t min_out_ring = 0)
+        : e_(e), b_(b), in_ring_(in_ring), out_ring_(out_ring), min_out_ring_(min_out_ring ? min_out_ring : out_ring), keep_(keep) {}
     ~HostSource() override { stop(DNALDPC_ERR_CUDA); }
 
     int prepare(Session &ss) {
         if (cudaSetDevice(e_.device()) != cudaSuccess) return set_fail(DNALDPC_ERR_CUDA, "cudaSetDevice failed");
         const size_t N = (size_t)b_.N, M = (size_t)b_.M;
-        bool ok = e_.stage(&e_.s_in_, &e_.c_in_, (size_t)in_ring_ * b_.packed) != nullptr;
-        ok = ok && e_.stage(&e_.s_iters_, &e_.c_iters_, (size_t)out_ring_ * 4);
-        ok = ok && e_.stage(&e_.s_ok_, &e_.c_ok_, (size_t)out_ring_);
-        if (b_.out.bits) ok = ok && e_.stage(&e_.s_bits_, &e_.c_bits_, (size_t)out_ring_ * b_.wpf * 4);
-        if (b_.out.dblk) ok = ok && e_.stage(&e_.s_dblk_, &e_.c_dblk_, (size_t)out_ring_ * N);
-        if (b_.out.posterior) ok = ok && e_.stage(&e_.s_post_, &e_.c_post_, (size_t)out_ring_ * N * 8);
-        if (b_.out.pchk) ok = ok && e_.stage(&e_.s_pchk_, &e_.c_pchk_, (size_t)out_ring_ * M);
+        bool ok = false;
+        for (;;) {  // a device short of memory gets a shorter output ring (admission then waits for stragglers sooner)
+            ok = e_.stage(&e_.s_in_, &e_.c_in_, (size_t)in_ring_ * b_.packed) != nullptr;
+            ok = ok && e_.stage(&e_.s_iters_, &e_.c_iters_, (size_t)out_ring_ * 4);
+            ok = ok && e_.stage(&e_.s_ok_, &e_.c_ok_, (size_t)out_ring_);
+            if (b_.out.bits) ok = ok && e_.stage(&e_.s_bits_, &e_.c_bits_, (size_t)out_ring_ * b_.wpf * 4);
+            if (b_.out.dblk) ok = ok && e_.stage(&e_.s_dblk_, &e_.c_dblk_, (size_t)out_ring_ * N);
+            if (b_.out.posterior) ok = ok && e_.stage(&e_.s_post_, &e_.c_post_, (size_t)out_ring_ * N * 8);
+            if (b_.out.pchk) ok = ok && e_.stage(&e_.s_pchk_, &e_.c_pchk_, (size_t)out_ring_ * M);
+            if (ok || out_ring_ <= min_out_ring_) break;
+            out_ring_ = std::max<int64_t>(min_out_ring_, round_up(out_ring_ / 2, b_.chunk));
+        }
         if (!ok) return set_fail(DNALDPC_ERR_NOMEM, "out of device memory (staging rings of a host batch)");
         if (b_.host_exp) {
             bounce_ = (double *)e_.pinned(2 * (size_t)b_.chunk * N * sizeof(double));
@@ -222,7 +228,7 @@ class HostSource : public FrameSource {
                 if (!cuda_ok(cudaMemcpy2DAsync(dst, b_.packed, src, b_.stride, b_.packed, (size_t)n, cudaMemcpyHostToDevice, st), "cudaMemcpy2DAsync(H2D)")) return;
             }
             const int rc = e_.publish(nullptr, (int)(q % in_ring_), (int)(q % out_ring_), n, st);
-            if (rc) { set_fail(rc, e_.error()); return; }
+            if (rc) { set_fail(rc, rc == DNALDPC_ERR_CUDA ? "CUDA error while publishing frames to the engine's queue" : "frame queue overflow"); return; }
             launches_++;
             {
                 std::lock_guard<std::mutex> lk(mu_);
@@ -279,7 +285,9 @@ class HostSource : public FrameSource {
 
     Engine &e_;
     HostBatch &b_;
-    const int64_t in_ring_, out_ring_;
+    const int64_t in_ring_;
+    int64_t out_ring_;
+    const int64_t min_out_ring_;
     const bool keep_;
     std::mutex mu_;
     std::condition_variable cv_;
@@ -346,11 +354,12 @@ int decode_host_batch(EngineSet &eng, const dnaldpc_input &in, int64_t F, int ma
     const int64_t in_ring = std::min(round_up(F, b.chunk), std::max<int64_t>(4 * b.chunk, wave));
     const int64_t budget = (int64_t)8 << 30;
     int64_t out_ring = std::min<int64_t>(262144, budget / (int64_t)out_bytes_per_frame(out, b.N, b.M));
-    out_ring = std::max<int64_t>(round_up(out_ring, b.chunk), std::max<int64_t>(4 * b.chunk, 2 * wave));
+    const int64_t min_out_ring = std::min(std::max<int64_t>(4 * b.chunk, 2 * wave), round_up(F, b.chunk));
+    out_ring = std::max<int64_t>(round_up(out_ring, b.chunk), min_out_ring);
     out_ring = std::min(out_ring, round_up(F, b.chunk));
     std::vector<std::unique_ptr<HostSource>> src;
     std::vector<Session> ss((size_t)nd);
-    for (int k = 0; k < nd; k++) src.emplace_back(new HostSource(*eng[(size_t)k], b, in_ring, out_ring, false));
+    for (int k = 0; k < nd; k++) src.emplace_back(new HostSource(*eng[(size_t)k], b, in_ring, out_ring, false, min_out_ring));
     std::vector<std::string> errs((size_t)nd);
     const int rc = run_engines(nd, [&](int k) {
         Engine &e = *eng[(size_t)k];
