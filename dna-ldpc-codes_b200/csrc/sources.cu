@@ -7,6 +7,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -316,6 +318,7 @@ int setup_host_batch(HostBatch &b, const EngineSet &eng, const dnaldpc_input &in
     // that every engine sees several chunks (dynamic balance); a multiple of 32 frames
     int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(2048, ((int64_t)32 << 20) / (int64_t)b.packed / 32 * 32));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(32, round_up((F + 4 * nd - 1) / (4 * nd), 32)));
+    if (const char *t = getenv("DNALDPC_CHUNK_FRAMES")) chunk = std::max<int64_t>(32, round_up(atoll(t), 32));  // test switch
     b.chunk = (int)chunk;
     b.n_chunks = (F + chunk - 1) / chunk;
     b.exp_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nd)));
@@ -357,9 +360,17 @@ int decode_host_batch(EngineSet &eng, const dnaldpc_input &in, int64_t F, int ma
     const int64_t min_out_ring = std::min(std::max<int64_t>(4 * b.chunk, 2 * wave), round_up(F, b.chunk));
     out_ring = std::max<int64_t>(round_up(out_ring, b.chunk), min_out_ring);
     out_ring = std::min(out_ring, round_up(F, b.chunk));
+    int64_t in_ring_used = in_ring, min_out_used = min_out_ring;
+    if (const char *t = getenv("DNALDPC_RING_CHUNKS")) {  // test switch "in,out": ring sizes in chunks, to force wrap-around on small batches
+        long a = 0, c = 0;
+        if (sscanf(t, "%ld,%ld", &a, &c) == 2 && a >= 1 && c >= 1) {
+            in_ring_used = a * b.chunk;
+            out_ring = min_out_used = c * b.chunk;
+        }
+    }
     std::vector<std::unique_ptr<HostSource>> src;
     std::vector<Session> ss((size_t)nd);
-    for (int k = 0; k < nd; k++) src.emplace_back(new HostSource(*eng[(size_t)k], b, in_ring, out_ring, false, min_out_ring));
+    for (int k = 0; k < nd; k++) src.emplace_back(new HostSource(*eng[(size_t)k], b, in_ring_used, out_ring, false, min_out_used));
     std::vector<std::string> errs((size_t)nd);
     const int rc = run_engines(nd, [&](int k) {
         Engine &e = *eng[(size_t)k];

@@ -355,3 +355,41 @@ def test_multi_device_dynamic_dispatch(code, cws):
     for key in ("bits", "iters", "ok", "rounds"):
         assert np.array_equal(s1[key], s2[key]), key
     one.close(); many.close()
+
+
+def test_staging_rings_wrap_around(code, orc, cws):
+    """Rings much shorter than the batch (test switches: 64-frame chunks, 2 chunks of input ring, 3 of output ring): every
+    ring row is reused dozens of times while frames that run to max_iter hold the low-water mark back, so admission
+    stalls on the output ring again and again. Results must not depend on any of it: compared with the default rings,
+    with the device-resident path and with the oracle; also through two GPUs when there are two."""
+    import torch
+    F = 4000
+    recv, lr, eps = _mixed_frames(cws, F, 123, (0.004, 0.006, 0.0075, 0.02))
+    packed = np.packbits(recv.astype(np.uint8), axis=1, bitorder="little").view(np.uint32)
+    t = ldpc.bsc_table(0.006)
+    dec = ldpc.Decoder(code, wave_frames=256)
+    ref = dec.decode(ldpc.IN_BSC_BITS, packed, 40, param=0.006, want=("bits", "dblk", "iters", "ok", "pchk"))
+    os.environ["DNALDPC_CHUNK_FRAMES"] = "64"
+    os.environ["DNALDPC_RING_CHUNKS"] = "2,3"
+    try:
+        a = dec.decode(ldpc.IN_BSC_BITS, packed, 40, param=0.006, want=("bits", "dblk", "iters", "ok", "pchk"))
+        b = dec.decode(ldpc.IN_LR_F64, t[recv], 40, want=("bits", "iters", "ok", "post"))
+        many = None
+        if torch.cuda.device_count() > 1:
+            d2 = ldpc.Decoder(code, devices=[0, 1], wave_frames=256)
+            many = d2.decode(ldpc.IN_BSC_BITS, packed, 40, param=0.006, want=("bits", "iters", "ok"))
+            d2.close()
+    finally:
+        del os.environ["DNALDPC_CHUNK_FRAMES"], os.environ["DNALDPC_RING_CHUNKS"]
+    for key in ("bits", "dblk", "iters", "ok", "pchk"):
+        assert np.array_equal(a[key], ref[key]), key
+    for key in ("bits", "iters", "ok"):
+        assert np.array_equal(b[key], ref[key]), key
+        if many is not None:
+            assert np.array_equal(many[key], ref[key]), key
+    assert (ref["iters"] == 40).sum() > 100 and (ref["iters"] < 10).sum() > 1000  # stragglers and fast frames interleaved
+    for f in list(range(0, F, 499)) + [int(np.argmax(ref["iters"]))]:
+        o = orc.decode(t[recv[f]], 40)
+        assert a["iters"][f] == o["n"] and np.array_equal(a["bits"][f], o["dblk"]), f
+        assert np.array_equal(b["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
+    dec.close()
