@@ -187,8 +187,9 @@ def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
     # the same frames through the host-buffer call (pinned memory, copies inside the timed region)
     Fh = 131072
     h_in = torch.empty((Fh, N), dtype=torch.int8).pin_memory(); h_in.copy_(d_in[:Fh])
+    same_size = run_device(dec, ldpc.IN_VOTE_I8, d_in[:Fh], Fh, 0.02, args.max_iter, N)  # the ratio compares batches of one size
     del d_in
-    out["c3_vote_i8_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_VOTE_I8, h_in, Fh, 0.02, args.max_iter, out["c3_vote_i8_1000000"])
+    out["c3_vote_i8_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_VOTE_I8, h_in, Fh, 0.02, args.max_iter, same_size)
     del h_in
     # configs[3]: AWGN at Eb/N0 = 4.6 dB
     F = 262144
@@ -198,8 +199,9 @@ def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
     out["c4_awgn_f32_%d" % F] = run_device(dec, ldpc.IN_AWGN_F32, d_in, F, sigma, args.max_iter, N)
     Fh = 65536
     h_in = torch.empty((Fh, N), dtype=torch.float32).pin_memory(); h_in.copy_(d_in[:Fh])
+    same_size = run_device(dec, ldpc.IN_AWGN_F32, d_in[:Fh], Fh, sigma, args.max_iter, N)
     del d_in
-    out["c4_awgn_f32_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_AWGN_F32, h_in, Fh, sigma, args.max_iter, out["c4_awgn_f32_%d" % F])
+    out["c4_awgn_f32_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_AWGN_F32, h_in, Fh, sigma, args.max_iter, same_size)
     del h_in
     # LLR text-file style input: fp64 LLRs, exp on the host with libm (what the CLI does); bound by libm exp on the host cores
     Fh = 16384
@@ -264,6 +266,7 @@ def host_leg(ldpc, torch, dec, kind, h_in, F, param, max_iter, device_ref, flags
          "avg_iters": fi / F, "h2d_bytes": h2d, "d2h_bytes": F * (W * 4 + 5), "pcie_gbs": (h2d + F * (W * 4 + 5)) / dt / 1e9}
     if device_ref is not None:
         r["vs_device_resident"] = r["frames_per_s"] / device_ref["frames_per_s"]
+        r["device_resident_frames_per_s"] = device_ref["frames_per_s"]  # same kind, same number of frames
     return r
 
 

@@ -162,6 +162,7 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     // A/B switches: DNALDPC_ROW_NO_TMEM=1 -> the one-item-per-warp shared-memory kernel; DNALDPC_ROW_L2HINT=0 -> bulk
     // copies without the evict-first policy.
     static const bool use_tmem = getenv("DNALDPC_ROW_NO_TMEM") == nullptr;
+    static const bool tmem32 = getenv("DNALDPC_ROW_TMEM32") != nullptr;
     static const int tm_hint = getenv("DNALDPC_ROW_L2HINT") ? atoi(getenv("DNALDPC_ROW_L2HINT")) : 1;
     if (use_smem && use_tmem && sizeof(T) == 8 && reg_rows_ && max_row_deg_ == 72) {
         // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
@@ -181,7 +182,7 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         }
         const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
         unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-#define TMROW(U, R) row_pass_tmem_kernel<72, U, R><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
+#define TMROW(U, R) row_pass_tmem_kernel<72, U, R><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
         // A/B switch DNALDPC_ROW_R16=1: in ticks that admit more than a quarter of the slots (frames of 2-4 iterations:
         // vote counts, AWGN at high SNR; more than 8 lanes of a group start per tick) use the variant that keeps 16 ranks
         // of the gather in flight (it fits at one block per trip). Measured: 368 k vs 371 k vote-count frames/s, 232 k
@@ -194,6 +195,23 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         else if (r16) TMROW(1, true);
         else TMROW(1, false);
 #undef TMROW
+    } else if (use_smem && use_tmem && tmem32 && sizeof(T) == 8 && max_row_deg_ <= 32 && max_row_deg_ > 8) {
+        // A/B switch DNALDPC_ROW_TMEM32=1: irregular rows of degree <= 32 (the n=65536 column-weight-3 code) through the
+        // same persistent tensor-memory pipeline with 8 KB tiles, 24 warps per SM, deg x 256-byte bulk copies. Measured
+        // (steady-state launch): 2.39 ms at one block per trip, 2.52 ms unrolled, against 2.45 ms for the one-item
+        // shared-memory kernel below - that code's check pass is not short of bytes in flight; off by default.
+        constexpr int W32 = 24;
+        const size_t smem = (size_t)W32 * 32 * kFG * sizeof(double) + W32 * sizeof(uint64_t) + (size_t)W32 * 32 * sizeof(int) + 16;
+        if (!tmem32_attr_set_) {
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<32, 4, false, false, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<32, 1, false, false, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tmem32_attr_set_ = true;
+        }
+        const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + W32 - 1) / W32);
+        unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
+        static const int ur32 = getenv("DNALDPC_ROW_UNROLL") ? atoi(getenv("DNALDPC_ROW_UNROLL")) : 1;
+        if (ur32 == 1) row_pass_tmem_kernel<32, 1, false, false, W32><<<pgrid, W32 * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
+        else row_pass_tmem_kernel<32, 4, false, false, W32><<<pgrid, W32 * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
     } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
         // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
         const bool big = reg_rows_ && max_row_deg_ == 72;
