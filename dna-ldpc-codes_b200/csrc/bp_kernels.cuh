@@ -352,99 +352,6 @@ row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const ui
     smem_row_compute<T, DC, EXACT>(col, base, lr_lane, col_idx + e0, fresh, deg);
 }
 
-// Persistent form of the shared-memory check pass. 3 CTAs x 4 warps stay resident per SM and pull JOBS from a device
-// counter: a job is one check i for a block of `gblock` consecutive groups. Per job the warp stages the check's column
-// indices in shared memory once, so the channel-ratio gather of the lanes that start a frame no longer waits for an
-// index load in every item (in the one-item-per-warp kernel that dependent pair of loads outlasts the 18 KB bulk copy
-// and sets the time a tile stays occupied); the slot masks of the next group are fetched while the current one is
-// worked on; and a tile is refilled as soon as ITS warp is done instead of when the last of the 4 warps of a CTA is.
-// One mbarrier per warp, phase-toggled; the tile is handed back to the async proxy with a proxy fence.
-template <typename T, int DC, bool EXACT = true>
-__global__ void __launch_bounds__(kRowWarps * 32, EXACT ? 3 : 6)
-row_pass_persist_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                        const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr,
-                        const int32_t *__restrict__ col_idx, int M, int N, int E, int g0, int G, int gblock,
-                        unsigned int *__restrict__ job_counter) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)warp * DC * kFG;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRowWarps * DC * kFG * sizeof(T)) + warp;
-    int *sidx = reinterpret_cast<int *>(smem_raw + (size_t)kRowWarps * DC * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t)) + warp * DC;
-    T *col = tile + lane;  // this lane's column of the tile: col[k * 32]
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    uint32_t phase = 0;
-    const int nblk = (G + gblock - 1) / gblock;
-    const unsigned njobs = (unsigned)M * (unsigned)nblk;
-    for (;;) {
-        unsigned job = 0;
-        if (lane == 0) job = atomicAdd(job_counter, 1u);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= njobs) break;
-        const int gb = (int)(job / (unsigned)M), i = (int)(job - (unsigned)gb * (unsigned)M);
-        const int e0 = EXACT ? i * DC : __ldg(row_ptr + i);
-        const int deg = EXACT ? DC : (__ldg(row_ptr + i + 1) - e0);
-        for (int k = lane; k < deg; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
-        __syncwarp();
-        int g = g0 + gb * gblock;
-        const int gend = min(g0 + G, g + gblock);
-        uint32_t act = actw[g], fw = freshw[g];
-        for (; g < gend; g++) {
-            uint32_t act_next = 0, fw_next = 0;
-            if (g + 1 < gend) { act_next = actw[g + 1]; fw_next = freshw[g + 1]; }  // in flight during this group's work
-            if (act != 0) {
-                const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
-                T *base = msg + ((size_t)g * E + e0) * kFG + lane;
-                const T *lr_base = lratio + (size_t)g * N * kFG;
-                const uint32_t fresh_mask = fw & act;
-                const bool streaming = (act & ~fresh_mask) != 0;  // warp-uniform
-                if (streaming && lane == 0) {
-                    mbar_expect_tx(bar, (uint32_t)(deg * kFG * sizeof(T)));
-                    tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, (uint32_t)(deg * kFG * sizeof(T)), bar);
-                }
-                if (fresh_mask == 0) {
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-                } else {
-                    // starting lanes: channel ratios of the check's bits, gathered by the whole warp, 8 ranks x 4 edges
-                    // per load instruction; the first 8 ranks travel together with the bulk copy
-                    constexpr int NT = (DC + 3) / 4;
-                    const int nf = __popc(fresh_mask);
-                    const int kq = lane >> 3;
-                    for (int r0 = 0; r0 < nf; r0 += 8) {
-                        const int r = r0 + (lane & 7);
-                        const bool mine = r < nf;
-                        const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
-                        T v[NT];
-#pragma unroll
-                        for (int t = 0; t < NT; t++) {
-                            const int k = t * 4 + kq;
-                            v[t] = (mine && k < deg) ? lr_base[(size_t)sidx[k] * kFG + f] : T(0);
-                        }
-                        if (r0 == 0 && streaming) {
-                            mbar_wait(bar, phase);
-                            phase ^= 1u;
-                        }
-#pragma unroll
-                        for (int t = 0; t < NT; t++) {
-                            const int k = t * 4 + kq;
-                            if (mine && k < deg) tile[k * kFG + f] = v[t];
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (on) smem_row_compute<T, DC, EXACT>(col, base, lr_base + lane, col_idx + e0, fresh, deg);
-                __syncwarp();  // every lane is done with the tile
-                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the next bulk write
-            }
-            act = act_next; fw = fw_next;
-        }
-    }
-}
-
 // ---- tensor memory (tcgen05) as a second on-chip tile ----------------------------------------------------
 // The check pass is bound by the bytes it can keep in flight per SM: 12 shared-memory tiles of 18 KB, each either being
 // filled or being worked on. The 256 KB of tensor memory per SM are idle in this kernel (no MMA anywhere), so the factors
@@ -508,20 +415,21 @@ constexpr int kTmWarps = 12;  // one CTA per SM: 12 tiles of shared memory, 3 wa
 //   pass 2 of k      : factors back from tensor memory block by block, lr_k streamed to the message array.
 // Both passes are loops over blocks of 8 edges, unrolled UR times (fully unrolled the kernel outgrows the instruction
 // cache and spends 15 % of a refill-regime launch waiting for instructions).
-template <int DC, int UR, bool R16, bool EXACT = true, int W = kTmWarps>
-__global__ void __launch_bounds__(W * 32, 1)
+template <int DC, int UR>
+__global__ void __launch_bounds__(kTmWarps * 32, 1)
 row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio, const uint32_t *__restrict__ actw,
-                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
-                     int M, int N, int E, int g0, int G, unsigned int *__restrict__ job_counter, int l2_hint) {
-    static_assert(DC % 8 == 0 && W % 4 == 0 && (DC / 8) * kTmBlockCols * (W / 4) <= 512, "tensor-memory columns");
+                     const uint32_t *__restrict__ freshw, const int32_t *__restrict__ col_idx, int M, int N, int E,
+                     int g0, int G, unsigned int *__restrict__ job_counter, int l2_hint) {
+    static_assert(DC % 8 == 0 && (DC / 8) * kTmBlockCols * (kTmWarps / 4) <= 512, "tensor-memory columns");
+    constexpr uint32_t kTileBytes = DC * kFG * sizeof(double);
     constexpr int NB = DC / 8, NT = DC / 4, NI = (DC + 31) / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *tile = reinterpret_cast<double *>(smem_raw) + (size_t)warp * DC * kFG;
-    unsigned char *aux = smem_raw + (size_t)W * DC * kFG * sizeof(double);
+    unsigned char *aux = smem_raw + (size_t)kTmWarps * DC * kFG * sizeof(double);
     uint64_t *bar = reinterpret_cast<uint64_t *>(aux) + warp;
-    int *sidx = reinterpret_cast<int *>(aux + W * sizeof(uint64_t)) + warp * DC;
-    uint32_t *tm_slot = reinterpret_cast<uint32_t *>(aux + W * sizeof(uint64_t) + (size_t)W * DC * sizeof(int));
+    int *sidx = reinterpret_cast<int *>(aux + kTmWarps * sizeof(uint64_t)) + warp * DC;
+    uint32_t *tm_slot = reinterpret_cast<uint32_t *>(aux + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * DC * sizeof(int));
     const double *col = tile + lane;
     const uint64_t policy = l2_evict_first_policy();
     if (warp == 0) tmem_alloc_512(tm_slot);
@@ -540,27 +448,20 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
     uint32_t phase = 0;
 
     // starts an item: bulk copy of its messages (if any lane carries on) and ranks 0..7 of the starting lanes' gather
-    auto start_item = [&](int g, int e0, int deg, uint32_t act, uint32_t fw, double (&v)[NT], double (&v2)[R16 ? NT : 1]) {
+    auto start_item = [&](int g, int e0, uint32_t act, uint32_t fw, double (&v)[NT]) {
         const uint32_t fresh_mask = fw & act;
         if ((act & ~fresh_mask) != 0 && lane == 0) {
-            const uint32_t bytes = (uint32_t)(deg * kFG * sizeof(double));  // irregular rows: the row's deg x 256 bytes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses to the tile before the bulk write
-            mbar_expect_tx(bar, bytes);
-            if (l2_hint) tma_load_1d_hint(tile, msg + ((size_t)g * E + e0) * kFG, bytes, bar, policy);
-            else tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, bytes, bar);
+            mbar_expect_tx(bar, kTileBytes);
+            if (l2_hint) tma_load_1d_hint(tile, msg + ((size_t)g * E + e0) * kFG, kTileBytes, bar, policy);
+            else tma_load_1d(tile, msg + ((size_t)g * E + e0) * kFG, kTileBytes, bar);
         }
         if (fresh_mask != 0) {
             const bool mine = rk < __popc(fresh_mask);
             const int f = nth_set_bit8(fresh_mask, rk);
             const double *lr_base = lratio + (size_t)g * N * kFG;
 #pragma unroll
-            for (int t = 0; t < NT; t++) v[t] = (mine && (EXACT || t * 4 + kq < deg)) ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
-            if (R16 && __popc(fresh_mask) > 8) {  // ranks 8..15 travel along as well (kinds with many starting lanes per tick)
-                const bool mine2 = rk + 8 < __popc(fresh_mask);
-                const int f2 = mine2 ? (int)__fns(fresh_mask, 0, rk + 9) : 0;
-#pragma unroll
-                for (int t = 0; t < (R16 ? NT : 1); t++) v2[t] = mine2 ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f2] : 0.0;
-            }
+            for (int t = 0; t < NT; t++) v[t] = mine ? lr_base[(size_t)sidx[t * 4 + kq] * kFG + f] : 0.0;
         }
     };
     auto claim_raw = [&]() -> unsigned {  // lane 0's register holds the item; nobody waits for it here
@@ -571,39 +472,31 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
 
     unsigned job = __shfl_sync(0xffffffffu, claim_raw(), 0);
     unsigned job_n = __shfl_sync(0xffffffffu, claim_raw(), 0);
-    int g = 0, e0 = 0, deg = DC;
+    int g = 0, e0 = 0;
     uint32_t act = 0, fw = 0;
-    double v[NT], v2[R16 ? NT : 1];
+    double v[NT];
     if (job < njobs) {  // the first item of this warp: nothing to overlap with yet
         g = g0 + (int)(job / (unsigned)M);
-        const int i = (int)(job % (unsigned)M);
-        e0 = EXACT ? i * DC : __ldg(row_ptr + i);
-        if (!EXACT) deg = __ldg(row_ptr + i + 1) - e0;
-        for (int k = lane; k < deg; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
+        e0 = (int)(job % (unsigned)M) * DC;
+        for (int k = lane; k < DC; k += 32) sidx[k] = __ldg(col_idx + e0 + k);
         __syncwarp();
         act = actw[g]; fw = freshw[g];
-        if (act != 0) start_item(g, e0, deg, act, fw, v, v2);
+        if (act != 0) start_item(g, e0, act, fw, v);
     }
     while (job < njobs) {
         // look ahead: claim the item after next; masks and column indices of the next item on their way
         const unsigned raw_nn = claim_raw();
         const bool valid_n = job_n < njobs;
-        const int g_n = g0 + (int)(job_n / (unsigned)M), i_n = (int)(job_n % (unsigned)M);
-        int e0_n = i_n * DC, e1_n = e0_n + DC;
+        const int g_n = g0 + (int)(job_n / (unsigned)M), e0_n = (int)(job_n % (unsigned)M) * DC;
         uint32_t act_n = 0, fw_n = 0;
         int idx_n[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) idx_n[q] = 0;
         if (valid_n) {
             act_n = actw[g_n]; fw_n = freshw[g_n];
-            if (EXACT) {
 #pragma unroll
-                for (int q = 0; q < NI; q++)
-                    if (lane + 32 * q < DC) idx_n[q] = __ldg(col_idx + e0_n + lane + 32 * q);
-            } else {  // irregular rows: where the row starts is itself a load; its column indices follow after pass 1
-                e0_n = __ldg(row_ptr + i_n);
-                e1_n = __ldg(row_ptr + i_n + 1);
-            }
+            for (int q = 0; q < NI; q++)
+                if (lane + 32 * q < DC) idx_n[q] = __ldg(col_idx + e0_n + lane + 32 * q);
         }
         const bool on = (act >> lane) & 1u, fresh = (fw >> lane) & 1u;
         double *base = msg + ((size_t)g * E + e0) * kFG + lane;
@@ -623,25 +516,18 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                     const int f = nth_set_bit8(fresh_mask, rk);
 #pragma unroll
                     for (int t = 0; t < NT; t++)
-                        if (mine && (EXACT || t * 4 + kq < deg)) tile[(t * 4 + kq) * kFG + f] = v[t];
+                        if (mine) tile[(t * 4 + kq) * kFG + f] = v[t];
                 }
-                if (R16 && nf > 8) {
-                    const bool mine = rk + 8 < nf;
-                    const int f = mine ? (int)__fns(fresh_mask, 0, rk + 9) : 0;
-#pragma unroll
-                    for (int t = 0; t < (R16 ? NT : 1); t++)
-                        if (mine) tile[(t * 4 + kq) * kFG + f] = v2[t];
-                }
-                for (int r0 = R16 ? 16 : 8; r0 < nf; r0 += 8) {  // still more starting lanes (first ticks of a batch): further rounds, not overlapped
+                for (int r0 = 8; r0 < nf; r0 += 8) {  // more than 8 starting lanes (first ticks of a batch, kinds with short frames): further rounds, not overlapped
                     const int r = r0 + rk;
                     const bool mine = r < nf;
                     const int f = mine ? (int)__fns(fresh_mask, 0, r + 1) : 0;
                     double w[NT];
 #pragma unroll
-                    for (int t = 0; t < NT; t++) w[t] = (mine && (EXACT || t * 4 + kq < deg)) ? lr_lane[(size_t)sidx[t * 4 + kq] * kFG + (f - lane)] : 0.0;
+                    for (int t = 0; t < NT; t++) w[t] = mine ? lr_lane[(size_t)sidx[t * 4 + kq] * kFG + (f - lane)] : 0.0;
 #pragma unroll
                     for (int t = 0; t < NT; t++)
-                        if (mine && (EXACT || t * 4 + kq < deg)) tile[(t * 4 + kq) * kFG + f] = w[t];
+                        if (mine) tile[(t * 4 + kq) * kFG + f] = w[t];
                 }
                 __syncwarp();
             }
@@ -653,8 +539,7 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                 const double ckb = B;
 #pragma unroll
                 for (int kk = 7; kk >= 0; kk--) {
-                    // padding edges of an irregular row: exact identities in both product chains, never read from the tile
-                    const double dk = (EXACT || b * 8 + kk < deg) ? check_factor(col[(b * 8 + kk) * kFG], bad) : 1.0;
+                    const double dk = check_factor(col[(b * 8 + kk) * kFG], bad);
                     d8[kk] = dk;
                     B = mul_rn(B, dk);
                 }
@@ -664,18 +549,13 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
         }
         __syncwarp();  // every lane has read its column and the staged indices: the tile and sidx can take the next item
         // start of the next item
-        const int deg_n = e1_n - e0_n;
-        if (EXACT) {
 #pragma unroll
-            for (int q = 0; q < NI; q++)
-                if (lane + 32 * q < DC) sidx[lane + 32 * q] = idx_n[q];
-        } else if (valid_n && (fw_n & act_n) != 0) {  // only a group with starting lanes needs the indices
-            for (int kx = lane; kx < deg_n; kx += 32) sidx[kx] = __ldg(col_idx + e0_n + kx);
-        }
+        for (int q = 0; q < NI; q++)
+            if (lane + 32 * q < DC) sidx[lane + 32 * q] = idx_n[q];
         __syncwarp();
-        if (valid_n && act_n != 0) start_item(g_n, e0_n, deg_n, act_n, fw_n, v, v2);
+        if (valid_n && act_n != 0) start_item(g_n, e0_n, act_n, fw_n, v);
         // (only `on`, `fresh`, `base`, `lr_lane`, `cols_cur`, `bad` still belong to the current item from here on)
-        if (on && bad) row_slow_path<double>(base, lr_lane, cols_cur, deg, fresh);  // invalid ratios: full IEEE divisions
+        if (on && bad) row_slow_path<double>(base, lr_lane, cols_cur, DC, fresh);  // invalid ratios: full IEEE divisions
         // pass 2, ascending: factors back from tensor memory, lr_k streamed to the message array
         if (act != 0) {
             double F = 1.0;
@@ -690,12 +570,12 @@ row_pass_tmem_kernel(double *__restrict__ msg, const double *__restrict__ lratio
                 for (int kk = 0; kk < 8; kk++) {
                     const double t = mul_rn(F, Bv[kk]);
                     const double lr = check_to_bit(t);
-                    if (store && (EXACT || b * 8 + kk < deg)) st_stream(base + (size_t)(b * 8 + kk) * kFG, lr);
+                    if (store) st_stream(base + (size_t)(b * 8 + kk) * kFG, lr);
                     F = mul_rn(F, d8[kk]);
                 }
             }
         }
-        job = job_n; g = g_n; e0 = e0_n; deg = deg_n; act = act_n; fw = fw_n;
+        job = job_n; g = g_n; e0 = e0_n; act = act_n; fw = fw_n;
         // pick up the claim made at the top (volatile: keeps its place behind pass 2, so the atomic's latency stays hidden)
         asm volatile("shfl.sync.idx.b32 %0, %1, 0, 31, 0xffffffff;" : "=r"(job_n) : "r"(raw_nn));
     }

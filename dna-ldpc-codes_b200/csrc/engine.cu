@@ -154,17 +154,13 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
     static const bool no_smem = getenv("DNALDPC_ROW_REGS") != nullptr;  // A/B switch: register-resident check kernel
     // A/B switch: the round-1 policy (smem-staged kernel only in ticks where every slot is busy and nobody is admitted)
     static const bool steady_only = getenv("DNALDPC_ROW_SMEM_STEADY_ONLY") != nullptr;
-    static const bool f32_smem = getenv("DNALDPC_ROW_SMEM_F32") != nullptr;  // A/B switch: TMA-staged check pass for fp32 too
-    const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && (sizeof(T) == 8 || f32_smem);
-    static const bool no_persist = getenv("DNALDPC_ROW_PERSIST") == nullptr;  // A/B switch: persistent form (measured: no gain)
-    static const int gblock = getenv("DNALDPC_ROW_GBLOCK") ? std::max(1, atoi(getenv("DNALDPC_ROW_GBLOCK"))) : 8;
+    const bool use_smem = !no_smem && (steady_ || !steady_only) && !minsum_ && sizeof(T) == 8;
     // Tensor memory as the second on-chip tile (row_pass_tmem_kernel): the default for the (.,72)-regular fp64 code.
     // A/B switches: DNALDPC_ROW_NO_TMEM=1 -> the one-item-per-warp shared-memory kernel; DNALDPC_ROW_L2HINT=0 -> bulk
     // copies without the evict-first policy.
     static const bool use_tmem = getenv("DNALDPC_ROW_NO_TMEM") == nullptr;
-    static const bool tmem32 = getenv("DNALDPC_ROW_TMEM32") != nullptr;
     static const int tm_hint = getenv("DNALDPC_ROW_L2HINT") ? atoi(getenv("DNALDPC_ROW_L2HINT")) : 1;
-    if (use_smem && use_tmem && sizeof(T) == 8 && reg_rows_ && max_row_deg_ == 72) {
+    if (use_smem && use_tmem && reg_rows_ && max_row_deg_ == 72) {
         // one CTA of 12 warps per SM; d_k parked in tensor memory so that the next check's bulk copy overlaps pass 2
         const size_t smem = (size_t)kTmWarps * 72 * kFG * sizeof(double) + kTmWarps * sizeof(uint64_t) + (size_t)kTmWarps * 72 * sizeof(int) + 16;
         // Blocks of 8 edges per loop trip. Same-box A/B (1.53 GHz under the power cap; steady-state step / refill-regime
@@ -174,60 +170,18 @@ template <typename T> int Engine::launch_row(int g0, int G, cudaStream_t st) {
         static const int ur_env = getenv("DNALDPC_ROW_UNROLL") ? atoi(getenv("DNALDPC_ROW_UNROLL")) : 0;
         const int ur = ur_env ? ur_env : (steady_ ? 9 : 3);
         if (!tmem_attr_set_) {
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<72, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             tmem_attr_set_ = true;
         }
         const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + kTmWarps - 1) / kTmWarps);
         unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-#define TMROW(U, R) row_pass_tmem_kernel<72, U, R><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
-        // A/B switch DNALDPC_ROW_R16=1: in ticks that admit more than a quarter of the slots (frames of 2-4 iterations:
-        // vote counts, AWGN at high SNR; more than 8 lanes of a group start per tick) use the variant that keeps 16 ranks
-        // of the gather in flight (it fits at one block per trip). Measured: 368 k vs 371 k vote-count frames/s, 232 k
-        // vs 233 k AWGN frames/s - the second gather round was not what those regimes wait for; off by default.
-        static const bool r16_on = getenv("DNALDPC_ROW_R16") != nullptr && atoi(getenv("DNALDPC_ROW_R16")) != 0;
-        const bool r16 = r16_on && many_fresh_;
-        if (r16 && !ur_env) TMROW(1, true);
-        else if (ur == 9) TMROW(9, false);
-        else if (ur == 3) TMROW(3, false);
-        else if (r16) TMROW(1, true);
-        else TMROW(1, false);
+#define TMROW(U) row_pass_tmem_kernel<72, U><<<pgrid, kTmWarps * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint)
+        if (ur == 9) TMROW(9);
+        else if (ur == 3) TMROW(3);
+        else TMROW(1);
 #undef TMROW
-    } else if (use_smem && use_tmem && tmem32 && sizeof(T) == 8 && max_row_deg_ <= 32 && max_row_deg_ > 8) {
-        // A/B switch DNALDPC_ROW_TMEM32=1: irregular rows of degree <= 32 (the n=65536 column-weight-3 code) through the
-        // same persistent tensor-memory pipeline with 8 KB tiles, 24 warps per SM, deg x 256-byte bulk copies. Measured
-        // (steady-state launch): 2.39 ms at one block per trip, 2.52 ms unrolled, against 2.45 ms for the one-item
-        // shared-memory kernel below - that code's check pass is not short of bytes in flight; off by default.
-        constexpr int W32 = 24;
-        const size_t smem = (size_t)W32 * 32 * kFG * sizeof(double) + W32 * sizeof(uint64_t) + (size_t)W32 * 32 * sizeof(int) + 16;
-        if (!tmem32_attr_set_) {
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<32, 4, false, false, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(row_pass_tmem_kernel<32, 1, false, false, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tmem32_attr_set_ = true;
-        }
-        const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_, (items + W32 - 1) / W32);
-        unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-        static const int ur32 = getenv("DNALDPC_ROW_UNROLL") ? atoi(getenv("DNALDPC_ROW_UNROLL")) : 1;
-        if (ur32 == 1) row_pass_tmem_kernel<32, 1, false, false, W32><<<pgrid, W32 * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
-        else row_pass_tmem_kernel<32, 4, false, false, W32><<<pgrid, W32 * 32, smem, st>>>((double *)msg, (const double *)lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, jobs, tm_hint);
-    } else if (use_smem && !no_persist && ((reg_rows_ && max_row_deg_ == 72) || (max_row_deg_ <= 32 && max_row_deg_ > 8))) {
-        // persistent check pass: resident warps pull (check, block of groups) jobs from a counter the syndrome kernel re-armed
-        const bool big = reg_rows_ && max_row_deg_ == 72;
-        const int dc = big ? 72 : 32;
-        const size_t smem = (size_t)kRowWarps * dc * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t) + (size_t)kRowWarps * dc * sizeof(int);
-        const unsigned pgrid = (unsigned)std::min<long long>((long long)sm_count_ * (big ? 3 : 6), (items + kRowWarps - 1) / kRowWarps);
-        unsigned *jobs = d_counters_ + (size_t)kRing * kCounterWords;
-        if (big) {
-            if (!persist_attr_set_) {
-                CK(cudaFuncSetAttribute(row_pass_persist_kernel<T, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                persist_attr_set_ = true;
-            }
-            row_pass_persist_kernel<T, 72><<<pgrid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, gblock, jobs);
-        } else {
-            row_pass_persist_kernel<T, 32, false><<<pgrid, kRowWarps * 32, smem, st>>>(msg, lr, s.actw, s.freshw, d_row_ptr_, d_col_idx_, M_, N_, E_, g0, G, gblock, jobs);
-        }
     } else if (use_smem && reg_rows_ && max_row_deg_ == 72) {
         // the (.,72)-regular sum-product hot path: check messages staged in shared memory by TMA, 12 warps per SM
         const size_t smem = (size_t)kRowWarps * 72 * kFG * sizeof(T) + kRowWarps * sizeof(uint64_t);
@@ -442,7 +396,6 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
     // the queue is empty and *avail == 0 from here on in stream order; producers on other streams wait for this point
     CK(cudaEventRecord(ready_ev_, st));
     steady_ = false;
-    many_fresh_ = false;
     traced_ = 0;
 
     // One tick = admit/harvest/check (twice) + one check-node pass + one bit-node pass over all slots.
@@ -506,7 +459,6 @@ int Engine::run(const Session &ss, FrameSource &src, cudaStream_t st) {
             if (final && admitted_total == published() && last_inuse == 0) break;  // drained: nothing active, unharvested or pending
             // steady state = every slot busy and nobody being admitted (e.g. long-running frames)
             steady_ = last_admitted == 0 && last_inuse >= (unsigned)S;
-            many_fresh_ = (long long)last_admitted * 4 > S;
             if (!final && last_inuse == 0 && admitted_total == published()) {
                 // Idle engine, starved source: do not spin empty ticks. The check / bit passes below still run: this tick's
                 // admission kernels are already queued and may pick up frames published meanwhile, and a slot's fresh mark

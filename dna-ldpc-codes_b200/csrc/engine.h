@@ -95,9 +95,8 @@ class Engine {
     int device_ = 0, precision_ = 0, wave_frames_ = 4096, sm_count_ = 148;
     int M_ = 0, N_ = 0, E_ = 0, max_row_deg_ = 0, max_col_deg_ = 0;
     bool reg_rows_ = false, reg_cols_ = false;
-    bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false, persist_attr_set_ = false, tmem_attr_set_ = false, tmem32_attr_set_ = false, syn_half_attr_set_ = false;
+    bool smem_attr_set_[2] = {false, false}, syn_attr_set_ = false, tmem_attr_set_ = false, syn_half_attr_set_ = false;
     bool steady_ = false;  // last polled tick: all slots busy, no frame admitted
-    bool many_fresh_ = false;  // last polled tick: more than a quarter of the slots admitted a frame
     bool minsum_ = false;  // current batch runs the LLR-domain min-sum rules instead of sum-product
     size_t esz_ = 8;
     // H edge tables (device)
