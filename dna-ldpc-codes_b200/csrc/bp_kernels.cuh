@@ -220,18 +220,47 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gsr
 template <typename T, int DC, bool EXACT = true>
 __device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_lane, const int32_t *cols, bool fresh, int deg = DC) {
     constexpr int NB = (DC + 7) / 8;
+    static_assert(EXACT || DC % 8 == 0, "irregular rows: the tile is a whole number of blocks");
     T ck[NB];
     T B = T(1);
     bool bad = false;
+    if (EXACT) {
 #pragma unroll
-    for (int k = DC - 1; k >= 0; k--) {
-        T dk = T(1);
-        if (EXACT || k < deg) {
-            dk = check_factor(col[k * kFG], bad);
+        for (int k = DC - 1; k >= 0; k--) {
+            const T dk = check_factor(col[k * kFG], bad);
             col[k * kFG] = dk;
+            if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
+            B = mul_rn(B, dk);
         }
-        if ((k & 7) == 7 || k == DC - 1) ck[k >> 3] = B;
-        B = mul_rn(B, dk);
+    } else {
+        // Irregular rows: `deg` is the same for the whole warp, so the blocks of 8 edges that lie entirely inside the row
+        // run the unpredicated code of the regular kernel behind ONE warp-uniform branch; only the row's last, partial
+        // block carries per-edge predicates, and blocks of pure padding are skipped (their factors are exact ones).
+        // (Per-edge predicates everywhere cost 65 instead of 41 instructions per edge, and under the power cap the
+        // n=65536 code's check pass is bound by instruction issue.)
+#pragma unroll
+        for (int b = NB - 1; b >= 0; b--) {
+            const int bot = b * 8;
+            ck[b] = B;
+            if (bot + 8 <= deg) {
+#pragma unroll
+                for (int k = bot + 7; k >= bot; k--) {
+                    const T dk = check_factor(col[k * kFG], bad);
+                    col[k * kFG] = dk;
+                    B = mul_rn(B, dk);
+                }
+            } else if (bot < deg) {
+#pragma unroll
+                for (int k = bot + 7; k >= bot; k--) {
+                    T dk = T(1);
+                    if (k < deg) {
+                        dk = check_factor(col[k * kFG], bad);
+                        col[k * kFG] = dk;
+                    }
+                    B = mul_rn(B, dk);
+                }
+            }
+        }
     }
     if (bad) {  // invalid likelihood ratios: nothing stored to msg yet, redo with full IEEE divisions
         row_slow_path<T>(base, lr_lane, cols, deg, fresh);
@@ -243,27 +272,33 @@ __device__ __forceinline__ void smem_row_compute(T *col, T *base, const T *lr_la
         const int bot = b * 8;
         const int top = (bot + 7 < DC - 1) ? bot + 7 : DC - 1;
         T d[8], Bv[8];
+        if (EXACT || bot + 8 <= deg) {
 #pragma unroll
-        for (int k = bot; k <= top; k++) d[k - bot] = (EXACT || k < deg) ? col[k * kFG] : T(1);
-        Bv[top - bot] = ck[b];
+            for (int k = bot; k <= top; k++) d[k - bot] = col[k * kFG];
+            Bv[top - bot] = ck[b];
 #pragma unroll
-        for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
+            for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
 #pragma unroll
-        for (int k = bot; k <= top; k++) {
-            const T t = mul_rn(F, Bv[k - bot]);
-            if (EXACT || k < deg) st_stream(base + (size_t)k * kFG, check_to_bit(t));
-            F = mul_rn(F, d[k - bot]);
+            for (int k = bot; k <= top; k++) {
+                const T t = mul_rn(F, Bv[k - bot]);
+                st_stream(base + (size_t)k * kFG, check_to_bit(t));
+                F = mul_rn(F, d[k - bot]);
+            }
+        } else if (bot < deg) {
+#pragma unroll
+            for (int k = bot; k <= top; k++) d[k - bot] = k < deg ? col[k * kFG] : T(1);
+            Bv[top - bot] = ck[b];
+#pragma unroll
+            for (int k = top; k > bot; k--) Bv[k - 1 - bot] = mul_rn(Bv[k - bot], d[k - bot]);
+#pragma unroll
+            for (int k = bot; k <= top; k++) {
+                const T t = mul_rn(F, Bv[k - bot]);
+                if (k < deg) st_stream(base + (size_t)k * kFG, check_to_bit(t));
+                F = mul_rn(F, d[k - bot]);
+            }
         }
     }
 }
-
-// Check pass with the check's 72 x 32 messages staged in shared memory (regular codes): ONE 18 KB cp.async.bulk per
-// warp lands the contiguous run in the warp's tile, the factors d_k overwrite the tile in place, and only the 9
-// check-pointed backward products plus one block of 8 factors live in registers. That takes the kernel from 254 to
-// <= 168 registers: 12 warps (3 CTAs, 3 x 73.8 KB of shared memory) per SM instead of 8, i.e. 50 % more bytes in flight.
-// Groups with slots that start a frame overwrite those lanes' columns of the tile with a warp-cooperative gather of the
-// channel ratios (below); idle lanes ride along in the bulk copy and are skipped.
-// EXACT = false (irregular rows of degree <= DC): the bulk copy takes the row's deg x 256 bytes; the tile stays DC rows.
 template <typename T, int DC, bool EXACT = true>
 __global__ void __launch_bounds__(kRowWarps * 32, EXACT ? 3 : 6)
 row_pass_smem_kernel(T *__restrict__ msg, const T *__restrict__ lratio, const uint32_t *__restrict__ actw,
