@@ -80,7 +80,7 @@ Engine::~Engine() {
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
                     d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_,
-                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1]};
+                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1], d_col_row_, d_sw_sched_, s_in2_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_bounce_) cudaFreeHost(h_bounce_);
@@ -88,6 +88,7 @@ Engine::~Engine() {
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
     for (auto &e : trace_ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : sw_in_ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
     for (auto &s : io_stream_) if (s) cudaStreamDestroy(s);
 }
@@ -627,6 +628,169 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
         CK(cudaMalloc((void **)&d_edge_row_, er.size() * sizeof(int32_t)));
         CK(cudaMemcpy(d_edge_row_, er.data(), er.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
+    if (!d_col_row_) {  // check of the k-th entry of a column (same order as col_edge)
+        std::vector<int32_t> cr((size_t)std::max(E_, 1));
+        std::vector<int32_t> er((size_t)std::max(E_, 1));
+        for (int i = 0; i < M_; i++)
+            for (int e = code.row_ptr[i]; e < code.row_ptr[i + 1]; e++) er[e] = i;
+        for (int k = 0; k < E_; k++) cr[k] = er[code.col_edge[k]];
+        CK(cudaMalloc((void **)&d_col_row_, cr.size() * sizeof(int32_t)));
+        CK(cudaMemcpy(d_col_row_, cr.data(), cr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    // A/B switch: the wave-lock-step schedule of the first version (every position runs until the slowest frame of the
+    // wave has left it) instead of continuous batching by group
+    if (getenv("DNALDPC_SW_LOCKSTEP") && atoi(getenv("DNALDPC_SW_LOCKSTEP")) != 0) return sw_lockstep(w, sched, lratio, F, max_iter, out, G);
+    return sw_groups(code, w, sched, lratio, F, max_iter, out, G);
+}
+
+// Continuous batching by group (sw_kernels.cuh, sw2_*): the frames of a chunk are staged in HBM (the next chunk's copy
+// runs meanwhile), the groups pull them 32 at a time from a device counter, every group walks through the window
+// positions at its own pace and a tick is one update of every group; the host counts harvested frames kLag ticks late.
+int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vector<int> &sched, const double *lratio, int64_t F,
+                      int max_iter, const dnaldpc_output &out, int G) {
+    cudaStream_t st = own_stream_, st_in = io_stream_[0];
+    const int L = w.L;
+    int max_rows = 0, max_cols = 0, max_init = 0;
+    for (int t = 0; t < L; t++) {
+        const int *r = &sched[(size_t)8 * t];
+        max_rows = std::max(max_rows, r[3] - r[2]);
+        max_cols = std::max(max_cols, r[1] - r[0]);
+        max_init = std::max(max_init, r[7] - r[6]);
+    }
+    // Does a check of some window ever touch a column Init_SW_Decoder has not reached yet? Then the zeros alloc_entry
+    // left in e->pr / e->lr are operands and a group's arrays are cleared for every new set of frames; for a window
+    // description that matches the code (every check's bits enter the window no later than the check) nothing a frame
+    // reads was written by the group's previous frames, and the 2 x E x 256 bytes per group stay untouched.
+    bool zero = false;
+    {
+        std::vector<int> init_at((size_t)N_, L);  // position at which a column is initialised
+        for (int t = 0; t < L; t++) {
+            const int *r = &sched[(size_t)8 * t];
+            for (int j = r[6]; j < r[7]; j++) init_at[(size_t)j] = std::min(init_at[(size_t)j], t);
+        }
+        std::vector<char> seen((size_t)M_, 0);
+        for (int t = 0; t < L && !zero; t++) {
+            const int *r = &sched[(size_t)8 * t];
+            for (int i = r[2]; i < r[3] && !zero; i++) {
+                if (seen[(size_t)i]) continue;  // a check's first position decides: columns are only ever added
+                seen[(size_t)i] = 1;
+                for (int e = code.row_ptr[i]; e < code.row_ptr[i + 1]; e++)
+                    if (init_at[(size_t)code.col_idx[e]] > t) { zero = true; break; }
+            }
+        }
+    }
+    if (getenv("DNALDPC_SW_ZERO") && atoi(getenv("DNALDPC_SW_ZERO")) != 0) zero = true;  // test switch
+    const uint32_t load_flags = SW_LOAD | SW_INIT | (zero ? SW_ZERO : 0u);
+    if (L > sw_cap_sched_) {
+        if (d_sw_sched_) cudaFree(d_sw_sched_);
+        d_sw_sched_ = nullptr; sw_cap_sched_ = 0;
+        CK(cudaMalloc((void **)&d_sw_sched_, (size_t)L * 8 * sizeof(int32_t)));
+        sw_cap_sched_ = L;
+    }
+    CK(cudaMemcpyAsync(d_sw_sched_, sched.data(), (size_t)L * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, st));  // pageable: staged before the call returns
+    SchedArrays sa;
+    fill_sched(sa);
+    SwGroups s;
+    s.run = sa.actw; s.valid = sa.donew; s.flags = sa.newfw; s.unsat = sa.freshw;
+    s.pos = (int32_t *)sa.harvw; s.frame0 = (int32_t *)sa.unsatw;
+    s.n_pos = sa.slot_iter; s.sum = sa.harv_iter;
+    s.sched = d_sw_sched_;
+    s.next_frame = d_next_; s.done = d_next_ + 1;
+    double *pr = (double *)d_msg_, *lr = (double *)d_sw_lr_, *lrat = (double *)d_lratio_;
+    const size_t wpf = (size_t)(N_ + 31) / 32;
+    // chunk of frames staged at a time: about 6 GB of input, at least the slots
+    const int64_t S = (int64_t)G * kFG;
+    int64_t chunk = std::max<int64_t>(S, ((int64_t)6 << 30) / ((int64_t)N_ * 8) / 32 * 32);
+    if (const char *t = getenv("DNALDPC_SW_CHUNK")) chunk = std::max<int64_t>(32, atoll(t) / 32 * 32);  // test switch
+    chunk = std::min<int64_t>(chunk, (F + 31) / 32 * 32);
+    const bool two = F > chunk;
+    void **in_buf[2] = {&s_in_, &s_in2_};
+    size_t *in_cap[2] = {&c_in_, &c_in2_};
+    for (int b = 0; b < (two ? 2 : 1); b++)
+        if (!stage(in_buf[b], in_cap[b], (size_t)std::min<int64_t>(chunk, F) * N_ * 8)) return fail("out of device memory (input staging)", DNALDPC_ERR_NOMEM);
+    if (!sw_in_ev_[0])
+        for (auto &e : sw_in_ev_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    auto upload = [&](int64_t f0, int b) -> int {
+        const int64_t nf = std::min<int64_t>(chunk, F - f0);
+        CK(cudaMemcpyAsync(*in_buf[b], lratio + (size_t)f0 * N_, (size_t)nf * N_ * 8, cudaMemcpyHostToDevice, st_in));
+        CK(cudaEventRecord(sw_in_ev_[b], st_in));
+        return DNALDPC_OK;
+    };
+    int rc = upload(0, 0);
+    if (rc) return rc;
+    long long tick = 0;
+    int b = 0;
+    for (int64_t f0 = 0; f0 < F; f0 += chunk, b ^= 1) {
+        const int nf = (int)std::min<int64_t>(chunk, F - f0);
+        const int Gc = (int)std::min<int64_t>(G, (nf + 31) / 32);
+        dnaldpc_output o{};
+        if (out.bits && !(o.bits = (uint32_t *)stage(&s_bits_, &c_bits_, (size_t)nf * wpf * 4))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        if (out.dblk && !(o.dblk = (uint8_t *)stage(&s_dblk_, &c_dblk_, (size_t)nf * N_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        if (out.pchk && !(o.pchk = (uint8_t *)stage(&s_pchk_, &c_pchk_, (size_t)nf * M_))) return fail("out of device memory", DNALDPC_ERR_NOMEM);
+        rc = ensure_frame_scratch(nf);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(st, sw_in_ev_[b], 0));
+        if (f0 + chunk < F) {  // the other buffer's last reader (the chunk before this one) has drained: see the sync below
+            rc = upload(f0 + chunk, b ^ 1);
+            if (rc) return rc;
+        }
+        const double *in = (const double *)*in_buf[b];
+        CK(cudaMemsetAsync(d_next_, 0, 3 * sizeof(unsigned long long), st));
+        const unsigned claim_grid = (unsigned)((Gc * kFG + 255) / 256);
+        sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 1, load_flags, d_iters_, d_ok_);
+        stats.kernel_launches++;
+        const unsigned load_x = (unsigned)((N_ + 31) / 32);
+        const long long row_items = (long long)Gc * max_rows;
+        bool done = false;
+        for (long long t0 = tick; !done; tick++) {
+            sw2_load_kernel<<<dim3(load_x, (unsigned)Gc), 256, 0, st>>>(in, lrat, d_decw_, s, N_);
+            if (zero) sw2_zero_kernel<<<dim3(64, (unsigned)Gc), 256, 0, st>>>(pr, lr, s, E_);
+            if (max_init > 0) sw2_init_kernel<<<dim3((unsigned)((max_init + 7) / 8), (unsigned)Gc), 256, 0, st>>>(pr, lr, lrat, s, d_col_ptr_, d_col_edge_, N_, E_);
+            if (max_rows > 0) {
+                const unsigned grid = (unsigned)((row_items + 3) / 4);
+                if (max_row_deg_ <= 8) sw2_row_kernel<8><<<grid, 128, 0, st>>>(pr, lr, s, d_row_ptr_, E_, max_rows, Gc);
+                else sw2_row_kernel<0><<<grid, 128, 0, st>>>(pr, lr, s, d_row_ptr_, E_, max_rows, Gc);
+            }
+            if (max_cols > 0) {
+                const dim3 grid((unsigned)((max_cols + 7) / 8), (unsigned)Gc);
+                if (max_col_deg_ <= 4) sw2_col_kernel<4><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
+                else if (max_col_deg_ <= 8) sw2_col_kernel<8><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
+                else sw2_col_kernel<0><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
+            }
+            sw2_syn_kernel<<<Gc, 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, N_, max_iter, L);
+            sw2_final_syn_kernel<<<dim3(kSwFinalSplit, (unsigned)Gc), 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, N_, M_, o.pchk);
+            if (o.bits || o.dblk) sw2_output_kernel<<<dim3((unsigned)((wpf + 7) / 8), (unsigned)Gc), 256, 0, st>>>(d_decw_, s, N_, (int)wpf, o.bits, o.dblk);
+            sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 0, load_flags, d_iters_, d_ok_);
+            stats.kernel_launches += 9;
+            stats.waves++;  // ticks
+            unsigned *hc = h_counters_ + kCounterWords * (tick % kRing);
+            CK(cudaMemcpyAsync(hc, d_next_ + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ev_[tick % kRing], st));
+            if (tick - t0 >= kLag) {
+                const long long tl = tick - kLag;
+                CK(cudaEventSynchronize(ev_[tl % kRing]));
+                unsigned long long dn = 0;
+                memcpy(&dn, h_counters_ + kCounterWords * (tl % kRing), sizeof(dn));
+                done = dn >= (unsigned long long)nf;
+            }
+        }
+        CK(cudaGetLastError());
+        if (out.bits) CK(cudaMemcpyAsync(out.bits + (size_t)f0 * wpf, o.bits, (size_t)nf * wpf * 4, cudaMemcpyDeviceToHost, st));
+        if (out.dblk) CK(cudaMemcpyAsync(out.dblk + (size_t)f0 * N_, o.dblk, (size_t)nf * N_, cudaMemcpyDeviceToHost, st));
+        if (out.pchk) CK(cudaMemcpyAsync(out.pchk + (size_t)f0 * M_, o.pchk, (size_t)nf * M_, cudaMemcpyDeviceToHost, st));
+        if (out.iters) CK(cudaMemcpyAsync(out.iters + f0, d_iters_, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        if (out.is_codeword) CK(cudaMemcpyAsync(out.is_codeword + f0, d_ok_, (size_t)nf, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (out.iters) for (int64_t f = 0; f < F; f++) stats.frame_iters += out.iters[f];
+    return DNALDPC_OK;
+}
+
+// The first version's schedule: the frames of a wave walk through the positions together.
+int Engine::sw_lockstep(const dnaldpc_window &w, const std::vector<int> &sched, const double *lratio, int64_t F, int max_iter,
+                        const dnaldpc_output &out, int G) {
+    cudaStream_t st = own_stream_;
+    int rc = DNALDPC_OK;
     SchedArrays s;
     fill_sched(s);
     uint32_t *runw = s.actw;

@@ -79,6 +79,10 @@ class Engine {
 
   private:
     template <typename T> int run(const Session &ss, FrameSource &src, cudaStream_t st);
+    int sw_groups(const Code &code, const dnaldpc_window &w, const std::vector<int> &sched, const double *lratio, int64_t F,
+                  int max_iter, const dnaldpc_output &out, int G);
+    int sw_lockstep(const dnaldpc_window &w, const std::vector<int> &sched, const double *lratio, int64_t F, int max_iter,
+                    const dnaldpc_output &out, int G);
     int ensure_rows(int64_t frames);
     template <typename T> int launch_row(int g0, int G, cudaStream_t st);
     template <typename T> int launch_col(int g0, int G, bool want_post, cudaStream_t st);
@@ -110,6 +114,10 @@ class Engine {
     void *d_sw_lr_ = nullptr;                            // sliding-window mode: second message array (check -> bit)
     int sw_cap_groups_ = 0;
     int32_t *d_edge_row_ = nullptr;                      // sliding-window mode: check of every edge
+    int32_t *d_col_row_ = nullptr;                       // sliding-window mode: check of the k-th entry of a column
+    int32_t *d_sw_sched_ = nullptr;                      // sliding-window mode: window ranges per position [L][8]
+    int sw_cap_sched_ = 0;
+    cudaEvent_t sw_in_ev_[2] = {nullptr, nullptr};       // sliding-window mode: a chunk's inputs have arrived
     int32_t *d_mv_ = nullptr;                            // drain-tail compaction: src[S], dst[S], {count, K}
     // compact when busy slots <= 15/16 of the packed region: a move is cheap next to the ticks it shortens (measured
     // thresholds 30 / 50 / 70 / 85 / 92 / 97 %: 16 384 frames eps 0.008 1196 / 1110 / 1084 / 1037 / 1016 / 992 ms per batch)
@@ -140,6 +148,8 @@ class Engine {
   public:
     // device staging of the host-pointer paths (owned here so that it is reused across calls; managed by the sources)
     void *stage(void **buf, size_t *cap, size_t need);
+    void *s_in2_ = nullptr;  // sliding-window mode: second input buffer (the next chunk's copy overlaps the decoding)
+    size_t c_in2_ = 0;
     void *s_in_ = nullptr, *s_bits_ = nullptr, *s_dblk_ = nullptr, *s_post_ = nullptr, *s_pchk_ = nullptr, *s_iters_ = nullptr, *s_ok_ = nullptr;
     size_t c_in_ = 0, c_bits_ = 0, c_dblk_ = 0, c_post_ = 0, c_pchk_ = 0, c_iters_ = 0, c_ok_ = 0;
     void *h_bounce_ = nullptr;   // pinned host memory (host-side exp of LLR batches, small result read-backs)

@@ -254,6 +254,378 @@ sw_syn_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ runw, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Continuous batching by GROUP (round 2, second half). The lock-step kernels above walk a whole wave through the
+// positions together, so every position runs until the slowest of up to 4096 frames is done. Here every group of 32
+// frames has its own window position: sw2_syn_kernel moves a group on as soon as ITS slowest frame has left the
+// position, a group whose last position is done is harvested (closing check(), outputs) and takes the next 32 pending
+// frames from one device counter. A tick is one update of every group at its own position; the host only counts
+// finished frames, a few ticks late. Per (check, frame) and (bit, frame) the arithmetic is that of the kernels above.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SW_LOAD = 1u, SW_INIT = 2u, SW_FINAL = 4u, SW_ZERO = 8u;
+
+struct SwGroups {
+    int32_t *pos;        // [G] window position of the group, L = no frames
+    uint32_t *run;       // [G] lanes that still iterate at this position
+    uint32_t *valid;     // [G] lanes that hold a frame
+    uint32_t *flags;     // [G] SW_LOAD / SW_ZERO / SW_INIT: work for the head of the next tick; SW_FINAL: harvest me
+    uint32_t *unsat;     // [G] OR over the checks of the closing syndrome, bit = lane
+    int32_t *frame0;     // [G] first frame (row of the staged chunk) of the group's frames
+    int32_t *n_pos;      // [G*32] extra updates run at this position (Iter_SW_Decoder's n)
+    int32_t *sum;        // [G*32] sum of n over the positions done
+    const int32_t *sched;  // [L*8] window ranges per position (engine.cu:sw_schedule)
+    unsigned long long *next_frame, *done;  // claim counter, frames harvested
+};
+
+// Harvest bookkeeping + admission, one warp per group (lane = slot). first != 0: start of a chunk, nothing to harvest.
+__global__ void __launch_bounds__(256)
+sw2_claim_kernel(SwGroups s, int G, int L, int F, int first, uint32_t load_flags, int32_t *__restrict__ iters_out,
+                 uint8_t *__restrict__ ok_out) {
+    const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= G) return;
+    const int slot = g * kFG + lane;
+    if (!first) {
+        if (!(s.flags[g] & SW_FINAL)) return;
+        const uint32_t v = s.valid[g];
+        if ((v >> lane) & 1u) {
+            const int f = s.frame0[g] + lane;
+            ok_out[f] = (uint8_t)(((s.unsat[g] >> lane) & 1u) ^ 1u);
+            iters_out[f] = s.sum[slot] / L;  // dec.cpp:2193-2194
+        }
+        if (lane == 0) atomicAdd(s.done, (unsigned long long)__popc(v));
+    }
+    unsigned long long f0 = 0;
+    if (lane == 0) f0 = atomicAdd(s.next_frame, 32ull);
+    f0 = __shfl_sync(0xffffffffu, f0, 0);
+    s.n_pos[slot] = 0;
+    s.sum[slot] = 0;
+    __syncwarp();  // every lane has read the old frames' state
+    if (lane == 0) {
+        if (f0 < (unsigned long long)F) {
+            const int left = F - (int)f0;
+            const uint32_t v = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+            s.valid[g] = v; s.run[g] = v; s.pos[g] = 0; s.frame0[g] = (int)f0; s.unsat[g] = 0; s.flags[g] = load_flags;
+        } else {
+            s.valid[g] = 0; s.run[g] = 0; s.pos[g] = L; s.flags[g] = 0;
+        }
+    }
+}
+
+// A group's new frames: frame-major staged rows -> slot-interleaved lratio; every decision starts "set" (see sw_load_kernel).
+__global__ void __launch_bounds__(256)
+sw2_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint32_t *__restrict__ decw, SwGroups s, int N) {
+    const int g = blockIdx.y;
+    if (!(s.flags[g] & SW_LOAD)) return;
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j0 = blockIdx.x * 32;
+    const uint32_t v = s.valid[g];
+    const size_t f0 = (size_t)s.frame0[g];
+    for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit
+        const int j = j0 + tx;
+        tile[r][tx] = (((v >> r) & 1u) && j < N) ? in[(f0 + r) * N + j] : 1.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {  // r = bit, tx = slot
+        const int j = j0 + r;
+        if (j < N) {
+            lratio[((size_t)g * N + j) * kFG + tx] = tile[tx][r];
+            if (tx == 0) decw[(size_t)g * N + j] = 0xffffffffu;
+        }
+    }
+}
+
+// alloc_entry's e->pr = e->lr = 0 for a group's new frames (only for window descriptions under which an entry can be
+// read before Init_SW_Decoder has reached its column; the host decides, engine.cu).
+__global__ void __launch_bounds__(256)
+sw2_zero_kernel(double *__restrict__ pr, double *__restrict__ lr, SwGroups s, int E) {
+    const int g = blockIdx.y;
+    if (!(s.flags[g] & SW_ZERO)) return;
+    const size_t n2 = (size_t)E * kFG / 2;  // double2 elements per array
+    double2 *a = (double2 *)(pr + (size_t)g * E * kFG), *b = (double2 *)(lr + (size_t)g * E * kFG);
+    const double2 z = make_double2(0.0, 0.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        a[i] = z;
+        b[i] = z;
+    }
+}
+
+// Init_SW_Decoder for the columns that enter the window at the group's position.
+__global__ void __launch_bounds__(256)
+sw2_init_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *__restrict__ lratio, SwGroups s,
+                const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N, int E) {
+    const int lane = threadIdx.x & 31, g = blockIdx.y;
+    if (!(s.flags[g] & SW_INIT)) return;
+    const int32_t *r = s.sched + 8 * s.pos[g];
+    const int j = r[6] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= r[7]) return;
+    const double v = lratio[((size_t)g * N + j) * kFG + lane];
+    for (int k = __ldg(col_ptr + j); k < __ldg(col_ptr + j + 1); k++) {
+        const size_t idx = ((size_t)g * E + __ldg(col_edge + k)) * kFG + lane;
+        pr[idx] = v;
+        lr[idx] = 1.0;
+    }
+}
+
+// Check_Update_SW for the checks of the group's window. DC > 0: rows of degree <= DC in registers (sw_row_reg_kernel's
+// arithmetic); DC == 0: the generic loop (sw_row_kernel's).
+template <int DC>
+__global__ void __launch_bounds__(128)
+sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups s, const int32_t *__restrict__ row_ptr, int E,
+               int max_rows, int G) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= (long long)G * max_rows) return;
+    const int g = (int)(item / max_rows);
+    const uint32_t run = s.run[g];
+    if (run == 0) return;
+    const int32_t *r = s.sched + 8 * s.pos[g];
+    const int i = r[2] + (int)(item - (long long)g * max_rows);
+    if (i >= r[3] || !((run >> lane) & 1u)) return;
+    const int e0 = __ldg(row_ptr + i), deg = __ldg(row_ptr + i + 1) - e0;
+    const double *p = pr + ((size_t)g * E + e0) * kFG + lane;
+    double *l = lr + ((size_t)g * E + e0) * kFG + lane;
+    bool bad = DC == 0;
+    if (DC > 0) {
+        constexpr int D = DC > 0 ? DC : 1;
+        double d[D], Bv[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) d[k] = k < deg ? ld_stream(p + (size_t)k * kFG) : 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) d[k] = k < deg ? check_factor(d[k], bad) : 1.0;  // padding: exact identity in both chains
+        if (!bad) {
+            double B = 1.0;
+#pragma unroll
+            for (int k = D - 1; k >= 0; k--) {
+                Bv[k] = B;
+                B = __dmul_rn(B, d[k]);
+            }
+            double F = 1.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const double t = __dmul_rn(F, Bv[k]);
+                if (k < deg) st_stream(l + (size_t)k * kFG, check_to_bit(t));
+                F = __dmul_rn(F, d[k]);
+            }
+        }
+    }
+    if (bad) {  // generic rows, or operands outside the proven ranges: the full-range loop of sw_row_kernel
+        double dl = 1.0;
+        for (int k = 0; k < deg; k++) {
+            l[(size_t)k * kFG] = dl;
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+        }
+        dl = 1.0;
+        for (int k = deg - 1; k >= 0; k--) {
+            const double t = __dmul_rn(l[(size_t)k * kFG], dl);
+            l[(size_t)k * kFG] = check_to_bit_slow(t);
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+        }
+    }
+}
+
+// Variable_Update_SW + Decision_SW for the bits of the group's window (sw_col_kernel's arithmetic). DV > 0: columns of
+// degree <= DV with every load in flight before the first multiplication (col_row = check of the k-th entry of a
+// column, so that the in-window test needs no dependent lookup): P_k = lratio * lr_0 .. lr_{k-1} over the in-window
+// entries, pr_k = P_k * S_k with S the product from the other end - the values sw_col_kernel leaves in e->pr.
+template <int DV>
+__global__ void __launch_bounds__(256)
+sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
+               uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
+               const int32_t *__restrict__ col_row, int N, int E) {
+    const int lane = threadIdx.x & 31, g = blockIdx.y;
+    const uint32_t run = s.run[g];
+    if (run == 0) return;
+    const int32_t *r = s.sched + 8 * s.pos[g];
+    const int j = r[0] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= r[1]) return;
+    const int c0 = r[2], c1 = r[3];
+    const bool on = (run >> lane) & 1u;
+    const int k0 = __ldg(col_ptr + j), k1 = __ldg(col_ptr + j + 1);
+    double *p = pr + (size_t)g * E * kFG + lane;
+    const double *l = lr + (size_t)g * E * kFG + lane;
+    double acc = on ? lratio[((size_t)g * N + j) * kFG + lane] : 1.0;
+    if (DV > 0) {
+        constexpr int D = DV > 0 ? DV : 1;
+        int e[D];
+        bool in[D];
+        double lv[D], P[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            in[k] = false;
+            e[k] = 0;
+            if (k0 + k < k1) {
+                const int row = __ldg(col_row + k0 + k);
+                e[k] = __ldg(col_edge + k0 + k);
+                in[k] = row < c1 && row >= c0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) lv[k] = (on && in[k]) ? ld_stream(l + (size_t)e[k] * kFG) : 1.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            P[k] = acc;
+            if (in[k]) acc = __dmul_rn(acc, lv[k]);
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, acc <= 1.0);
+        if (lane == 0) {
+            uint32_t *dst = decw + (size_t)g * N + j;
+            *dst = (w & run) | (*dst & ~run);
+        }
+        double S = 1.0;
+#pragma unroll
+        for (int k = D - 1; k >= 0; k--) {
+            if (in[k]) {
+                double v = __dmul_rn(P[k], S);
+                if (v != v) v = 1.0;
+                if (on) st_stream(p + (size_t)e[k] * kFG, v);
+                S = __dmul_rn(S, lv[k]);
+            }
+        }
+        return;
+    }
+    if (on) {
+        for (int k = k0; k < k1; k++) {
+            const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+            if (row < c1 && row >= c0) {
+                p[(size_t)e * kFG] = acc;
+                acc = __dmul_rn(acc, l[(size_t)e * kFG]);
+            }
+        }
+    }
+    const uint32_t w = __ballot_sync(0xffffffffu, acc <= 1.0);
+    if (lane == 0) {
+        uint32_t *dst = decw + (size_t)g * N + j;
+        *dst = (w & run) | (*dst & ~run);
+    }
+    if (on) {
+        double sp = 1.0;
+        for (int k = k1 - 1; k >= k0; k--) {
+            const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+            if (row < c1 && row >= c0) {
+                double v = __dmul_rn(p[(size_t)e * kFG], sp);
+                if (v != v) v = 1.0;
+                p[(size_t)e * kFG] = v;
+                sp = __dmul_rn(sp, l[(size_t)e * kFG]);
+            }
+        }
+    }
+}
+
+// check_bound + the loop control of Iter_SW_Decoder (sw_syn_kernel) at the group's own position, and the step to the
+// next position once no frame of the group iterates any more. One CTA per group.
+__global__ void __launch_bounds__(256)
+sw2_syn_kernel(const uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ row_ptr,
+               const int32_t *__restrict__ col_idx, int N, int max_iter, int L) {
+    const int g = blockIdx.x;
+    const uint32_t run = s.run[g];
+    if (run == 0) return;
+    const int t = s.pos[g];
+    const int32_t *r = s.sched + 8 * t;
+    const int v0 = r[0], vc = r[4], c0 = r[2], cc = r[5];
+    const uint32_t *dw = decw + (size_t)g * N;
+    uint32_t acc = 0;
+    for (int i = c0 + threadIdx.x; i < cc; i += blockDim.x) {
+        uint32_t p = 0;
+        for (int e = __ldg(row_ptr + i); e < __ldg(row_ptr + i + 1); e++) {
+            const int c = __ldg(col_idx + e);
+            if (c >= v0 && c < vc) p ^= dw[c];
+        }
+        acc |= p;
+    }
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    __shared__ uint32_t s_or[8];
+    if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    uint32_t unsat = 0;
+    for (int w = 0; w < 8; w++) unsat |= s_or[w];
+    const int f = threadIdx.x, slot = g * kFG + f;
+    const bool running = (run >> f) & 1u;
+    bool cont = false;
+    int n = 0;
+    if (running) {
+        n = s.n_pos[slot];
+        if (n == max_iter || !((unsat >> f) & 1u)) s.sum[slot] += n;
+        else { n = n + 1; cont = true; }
+    }
+    const uint32_t next = __ballot_sync(0xffffffffu, cont);
+    if (next) {
+        if (cont) s.n_pos[slot] = n;
+        if (f == 0) { s.run[g] = next; s.flags[g] = 0; }
+    } else {  // the group's slowest frame has left position t
+        s.n_pos[slot] = 0;
+        if (f == 0) {
+            if (t + 1 < L) { s.pos[g] = t + 1; s.run[g] = s.valid[g]; s.flags[g] = SW_INIT; }
+            else { s.run[g] = 0; s.flags[g] = SW_FINAL; }
+        }
+    }
+}
+
+// The closing check() of Run_SW_Decoder (dec.cpp:2187-2189) for the groups that are through: kSwFinalSplit CTAs per
+// group, OR of the syndrome words into unsat[g], the syndrome bytes on request.
+constexpr int kSwFinalSplit = 8;
+__global__ void __launch_bounds__(256)
+sw2_final_syn_kernel(const uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ row_ptr,
+                     const int32_t *__restrict__ col_idx, int N, int M, uint8_t *__restrict__ pchk_out) {
+    const int g = blockIdx.y;
+    if (!(s.flags[g] & SW_FINAL)) return;
+    const uint32_t valid = s.valid[g];
+    const size_t f0 = (size_t)s.frame0[g];
+    const uint32_t *dw = decw + (size_t)g * N;
+    uint32_t acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        uint32_t p = 0;
+        for (int e = __ldg(row_ptr + i); e < __ldg(row_ptr + i + 1); e++) p ^= dw[__ldg(col_idx + e)];
+        acc |= p;
+        if (pchk_out)
+            for (uint32_t m = valid; m; m &= m - 1) {
+                const int f = __ffs(m) - 1;
+                pchk_out[(f0 + f) * M + i] = (uint8_t)((p >> f) & 1u);
+            }
+    }
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicOr(s.unsat + g, acc);
+}
+
+// Decisions of the groups that are through -> frame-major outputs. A warp takes 32 bits x 32 slots: bit f of its 32
+// decision words is frame f's word (32 ballots).
+__global__ void __launch_bounds__(256)
+sw2_output_kernel(const uint32_t *__restrict__ decw, SwGroups s, int N, int wpf, uint32_t *__restrict__ bits,
+                  uint8_t *__restrict__ dblk) {
+    const int g = blockIdx.y;
+    if (!(s.flags[g] & SW_FINAL)) return;
+    const int lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= wpf) return;
+    const uint32_t valid = s.valid[g];
+    const size_t f0 = (size_t)s.frame0[g];
+    const int j = w * 32 + lane;
+    const uint32_t mine = j < N ? decw[(size_t)g * N + j] : 0u;
+    uint32_t word = 0;
+#pragma unroll
+    for (int f = 0; f < 32; f++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (mine >> f) & 1u);
+        if (lane == f) word = b;
+    }
+    if (!((valid >> lane) & 1u)) return;
+    if (bits) bits[(f0 + lane) * wpf + w] = word;
+    if (dblk) {
+        uint8_t *d = dblk + (f0 + lane) * N + (size_t)w * 32;
+        const int nb = min(32, N - w * 32);
+        if (nb == 32 && (N & 15) == 0) {  // 16-byte aligned rows: two 16-byte stores
+            uint32_t q[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t nib = word >> (4 * i);
+                q[i] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            }
+            ((uint4 *)d)[0] = make_uint4(q[0], q[1], q[2], q[3]);
+            ((uint4 *)d)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+        } else {
+            for (int b = 0; b < nb; b++) d[b] = (uint8_t)((word >> b) & 1u);
+        }
+    }
+}
+
 // Decisions of a wave back to frame-major outputs (packed words and / or 0-1 chars).
 __global__ void __launch_bounds__(256)
 sw_output_kernel(const uint32_t *__restrict__ decw, int N, int nf, long long frame0, int wpf, uint32_t *__restrict__ bits,
