@@ -192,9 +192,41 @@ int dnaldpc_decode_window(dnaldpc_decoder *d, const dnaldpc_window *win, const d
                           const dnaldpc_output *out) {
     DeviceRestore restore_device;
     if (!d || !win || !out) return set_err(DNALDPC_ERR_ARG, "null argument");
-    const int rc = d->eng[0]->decode_window_host(d->c, *win, lratio, F, max_iter, *out);
-    if (rc) return set_err(rc, d->eng[0]->error());
-    d->stats = d->eng[0]->stats;
+    // Frames are independent (DNA_main.cpp:629-651 splits them over ranks): with several devices every engine decodes
+    // a contiguous share of the batch on its own thread, no exchange between them.
+    const int nd = (int)std::min<int64_t>((int64_t)d->eng.size(), std::max<int64_t>(1, F / 64));
+    if (nd <= 1) {
+        const int rc = d->eng[0]->decode_window_host(d->c, *win, lratio, F, max_iter, *out);
+        if (rc) return set_err(rc, d->eng[0]->error());
+        d->stats = d->eng[0]->stats;
+        return DNALDPC_OK;
+    }
+    const int N = d->c.N, M = d->c.M;
+    const size_t wpf = (size_t)(N + 31) / 32;
+    const int64_t share = ((F + nd - 1) / nd + 31) / 32 * 32;
+    std::vector<int> rcs((size_t)nd, DNALDPC_OK);
+    auto run = [&](int k) {
+        const int64_t f0 = std::min<int64_t>(F, share * k), nf = std::min<int64_t>(share, F - f0);
+        if (nf <= 0) { d->eng[(size_t)k]->stats = dnaldpc_stats{}; return; }
+        dnaldpc_output o = *out;
+        if (o.bits) o.bits += (size_t)f0 * wpf;
+        if (o.dblk) o.dblk += (size_t)f0 * N;
+        if (o.pchk) o.pchk += (size_t)f0 * M;
+        if (o.iters) o.iters += f0;
+        if (o.is_codeword) o.is_codeword += f0;
+        rcs[(size_t)k] = d->eng[(size_t)k]->decode_window_host(d->c, *win, lratio + (size_t)f0 * N, nf, max_iter, o);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nd; k++) th.emplace_back(run, k);
+    run(0);
+    for (auto &t : th) t.join();
+    d->stats = dnaldpc_stats{};
+    for (int k = 0; k < nd; k++) {
+        if (rcs[(size_t)k]) return set_err(rcs[(size_t)k], d->eng[(size_t)k]->error());
+        const dnaldpc_stats &e = d->eng[(size_t)k]->stats;
+        d->stats.frames += e.frames; d->stats.frame_iters += e.frame_iters; d->stats.kernel_launches += e.kernel_launches;
+        d->stats.waves += e.waves;
+    }
     return DNALDPC_OK;
 }
 

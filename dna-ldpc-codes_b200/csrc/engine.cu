@@ -80,7 +80,7 @@ Engine::~Engine() {
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
                     d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_,
-                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1], d_col_row_, d_sw_sched_, s_in2_};
+                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1], d_col_row_, d_sw_sched_, s_in2_, d_sw_avail_, d_sw_lists_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_bounce_) cudaFreeHost(h_bounce_);
@@ -710,14 +710,35 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
         if (!stage(in_buf[b], in_cap[b], (size_t)std::min<int64_t>(chunk, F) * N_ * 8)) return fail("out of device memory (input staging)", DNALDPC_ERR_NOMEM);
     if (!sw_in_ev_[0])
         for (auto &e : sw_in_ev_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!d_sw_avail_) CK(cudaMalloc((void **)&d_sw_avail_, 2 * sizeof(unsigned long long)));
+    if (G > sw_cap_lists_) {
+        if (d_sw_lists_) cudaFree(d_sw_lists_);
+        d_sw_lists_ = nullptr; sw_cap_lists_ = 0;
+        CK(cudaMalloc((void **)&d_sw_lists_, ((size_t)2 * G + 2) * sizeof(int32_t)));
+        sw_cap_lists_ = G;
+    }
+    // A chunk is copied in pieces of about 64 MB; behind every piece the copy stream publishes how many frames of the
+    // chunk are resident, and the groups only take frames that are (sw2_claim_kernel): decoding starts with the first
+    // piece, and the next chunk's copy runs while this one is decoded. (Pageable host memory: the copies block the
+    // calling thread, so they do not overlap the decoding; results are the same.)
+    int64_t piece = std::max<int64_t>(32, ((int64_t)64 << 20) / ((int64_t)N_ * 8) / 32 * 32);
+    if (const char *t = getenv("DNALDPC_SW_PIECE")) piece = std::max<int64_t>(32, atoll(t) / 32 * 32);  // test switch
     auto upload = [&](int64_t f0, int b) -> int {
         const int64_t nf = std::min<int64_t>(chunk, F - f0);
-        CK(cudaMemcpyAsync(*in_buf[b], lratio + (size_t)f0 * N_, (size_t)nf * N_ * 8, cudaMemcpyHostToDevice, st_in));
-        CK(cudaEventRecord(sw_in_ev_[b], st_in));
+        CK(cudaMemsetAsync(d_sw_avail_ + b, 0, sizeof(unsigned long long), st_in));
+        CK(cudaEventRecord(sw_in_ev_[b], st_in));  // the decoding of this chunk may start: nothing is resident yet
+        for (int64_t p0 = 0; p0 < nf; p0 += piece) {
+            const int64_t np = std::min<int64_t>(piece, nf - p0);
+            CK(cudaMemcpyAsync((double *)*in_buf[b] + (size_t)p0 * N_, lratio + (size_t)(f0 + p0) * N_, (size_t)np * N_ * 8, cudaMemcpyHostToDevice, st_in));
+            sw2_publish_kernel<<<1, 1, 0, st_in>>>(d_sw_avail_ + b, (unsigned long long)(p0 + np));
+            stats.kernel_launches++;
+        }
+        CK(cudaGetLastError());
         return DNALDPC_OK;
     };
     int rc = upload(0, 0);
     if (rc) return rc;
+    static const int packed = getenv("DNALDPC_SW_PACKED") ? atoi(getenv("DNALDPC_SW_PACKED")) : 1;  // A/B switch: 0 = a warp per node whatever the number of running frames
     long long tick = 0;
     int b = 0;
     for (int64_t f0 = 0; f0 < F; f0 += chunk, b ^= 1) {
@@ -735,33 +756,35 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
             if (rc) return rc;
         }
         const double *in = (const double *)*in_buf[b];
+        s.avail = d_sw_avail_ + b;
+        s.lists = d_sw_lists_;
         CK(cudaMemsetAsync(d_next_, 0, 3 * sizeof(unsigned long long), st));
         const unsigned claim_grid = (unsigned)((Gc * kFG + 255) / 256);
         sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 1, load_flags, d_iters_, d_ok_);
         stats.kernel_launches++;
-        const unsigned load_x = (unsigned)((N_ + 31) / 32);
-        const long long row_items = (long long)Gc * max_rows;
+        const unsigned load_x = (unsigned)((N_ + 31) / 32), head_y = (unsigned)std::min(Gc, 4);
         bool done = false;
         for (long long t0 = tick; !done; tick++) {
-            sw2_load_kernel<<<dim3(load_x, (unsigned)Gc), 256, 0, st>>>(in, lrat, d_decw_, s, N_);
-            if (zero) sw2_zero_kernel<<<dim3(64, (unsigned)Gc), 256, 0, st>>>(pr, lr, s, E_);
-            if (max_init > 0) sw2_init_kernel<<<dim3((unsigned)((max_init + 7) / 8), (unsigned)Gc), 256, 0, st>>>(pr, lr, lrat, s, d_col_ptr_, d_col_edge_, N_, E_);
+            sw2_list_kernel<<<1, 1024, 0, st>>>(s, Gc);
+            sw2_load_kernel<<<dim3(load_x, head_y), 256, 0, st>>>(in, lrat, d_decw_, s, N_, Gc);
+            if (zero) sw2_zero_kernel<<<dim3(64, head_y), 256, 0, st>>>(pr, lr, s, E_, Gc);
+            if (max_init > 0) sw2_init_kernel<<<dim3((unsigned)((max_init + 7) / 8), head_y), 256, 0, st>>>(pr, lr, lrat, s, d_col_ptr_, d_col_edge_, N_, E_, Gc);
             if (max_rows > 0) {
-                const unsigned grid = (unsigned)((row_items + 3) / 4);
-                if (max_row_deg_ <= 8) sw2_row_kernel<8><<<grid, 128, 0, st>>>(pr, lr, s, d_row_ptr_, E_, max_rows, Gc);
-                else sw2_row_kernel<0><<<grid, 128, 0, st>>>(pr, lr, s, d_row_ptr_, E_, max_rows, Gc);
+                const dim3 grid((unsigned)((max_rows + kSwNodesPerCta - 1) / kSwNodesPerCta), (unsigned)Gc);
+                if (max_row_deg_ <= 8) sw2_row_kernel<8><<<grid, 256, 0, st>>>(pr, lr, s, d_row_ptr_, E_, packed);
+                else sw2_row_kernel<0><<<grid, 256, 0, st>>>(pr, lr, s, d_row_ptr_, E_, packed);
             }
             if (max_cols > 0) {
-                const dim3 grid((unsigned)((max_cols + 7) / 8), (unsigned)Gc);
-                if (max_col_deg_ <= 4) sw2_col_kernel<4><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
-                else if (max_col_deg_ <= 8) sw2_col_kernel<8><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
-                else sw2_col_kernel<0><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_);
+                const dim3 grid((unsigned)((max_cols + kSwNodesPerCta - 1) / kSwNodesPerCta), (unsigned)Gc);
+                if (max_col_deg_ <= 4) sw2_col_kernel<4><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_, packed);
+                else if (max_col_deg_ <= 8) sw2_col_kernel<8><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_, packed);
+                else sw2_col_kernel<0><<<grid, 256, 0, st>>>(pr, lr, lrat, d_decw_, s, d_col_ptr_, d_col_edge_, d_col_row_, N_, E_, packed);
             }
             sw2_syn_kernel<<<Gc, 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, N_, max_iter, L);
             sw2_final_syn_kernel<<<dim3(kSwFinalSplit, (unsigned)Gc), 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, N_, M_, o.pchk);
             if (o.bits || o.dblk) sw2_output_kernel<<<dim3((unsigned)((wpf + 7) / 8), (unsigned)Gc), 256, 0, st>>>(d_decw_, s, N_, (int)wpf, o.bits, o.dblk);
             sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 0, load_flags, d_iters_, d_ok_);
-            stats.kernel_launches += 9;
+            stats.kernel_launches += 10;
             stats.waves++;  // ticks
             unsigned *hc = h_counters_ + kCounterWords * (tick % kRing);
             CK(cudaMemcpyAsync(hc, d_next_ + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

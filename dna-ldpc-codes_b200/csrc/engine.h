@@ -117,6 +117,9 @@ class Engine {
     int32_t *d_col_row_ = nullptr;                       // sliding-window mode: check of the k-th entry of a column
     int32_t *d_sw_sched_ = nullptr;                      // sliding-window mode: window ranges per position [L][8]
     int sw_cap_sched_ = 0;
+    unsigned long long *d_sw_avail_ = nullptr;           // sliding-window mode: frames resident per input buffer [2]
+    int32_t *d_sw_lists_ = nullptr;                      // sliding-window mode: per-tick work lists [2][G] + 2 counts
+    int sw_cap_lists_ = 0;
     cudaEvent_t sw_in_ev_[2] = {nullptr, nullptr};       // sliding-window mode: a chunk's inputs have arrived
     int32_t *d_mv_ = nullptr;                            // drain-tail compaction: src[S], dst[S], {count, K}
     // compact when busy slots <= 15/16 of the packed region: a move is cheap next to the ticks it shortens (measured

@@ -262,22 +262,48 @@ sw_syn_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ runw, in
 // frames from one device counter. A tick is one update of every group at its own position; the host only counts
 // finished frames, a few ticks late. Per (check, frame) and (bit, frame) the arithmetic is that of the kernels above.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t SW_LOAD = 1u, SW_INIT = 2u, SW_FINAL = 4u, SW_ZERO = 8u;
+constexpr uint32_t SW_LOAD = 1u, SW_INIT = 2u, SW_FINAL = 4u, SW_ZERO = 8u, SW_WANT = 16u;
 
 struct SwGroups {
     int32_t *pos;        // [G] window position of the group, L = no frames
     uint32_t *run;       // [G] lanes that still iterate at this position
     uint32_t *valid;     // [G] lanes that hold a frame
-    uint32_t *flags;     // [G] SW_LOAD / SW_ZERO / SW_INIT: work for the head of the next tick; SW_FINAL: harvest me
+    uint32_t *flags;     // [G] SW_LOAD / SW_ZERO / SW_INIT: work for the head of the next tick; SW_FINAL: harvest me;
+                         //     SW_WANT: empty, waiting for frames that are still on their way to the device
     uint32_t *unsat;     // [G] OR over the checks of the closing syndrome, bit = lane
     int32_t *frame0;     // [G] first frame (row of the staged chunk) of the group's frames
     int32_t *n_pos;      // [G*32] extra updates run at this position (Iter_SW_Decoder's n)
     int32_t *sum;        // [G*32] sum of n over the positions done
     const int32_t *sched;  // [L*8] window ranges per position (engine.cu:sw_schedule)
     unsigned long long *next_frame, *done;  // claim counter, frames harvested
+    const unsigned long long *avail;        // frames of the chunk that have arrived in HBM (sw2_publish_kernel)
+    int32_t *lists;      // [2][G] groups flagged SW_LOAD / SW_INIT in this tick, [2G], [2G+1] their counts (sw2_list_kernel)
 };
 
+// The copy stream says how many frames of the chunk are resident (ordered behind the copy that brought them).
+__global__ void sw2_publish_kernel(unsigned long long *avail, unsigned long long frames) {
+    *(volatile unsigned long long *)avail = frames;
+    __threadfence();
+}
+
+// Work lists of a tick's head: the few groups that take new frames / start a position (the load / init kernels then
+// walk these instead of launching a CTA per (group, tile) that finds nothing to do).
+__global__ void __launch_bounds__(1024)
+sw2_list_kernel(SwGroups s, int G) {
+    __shared__ int n[2];
+    if (threadIdx.x < 2) n[threadIdx.x] = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const uint32_t f = s.flags[g];
+        if (f & SW_LOAD) s.lists[atomicAdd(&n[0], 1)] = g;
+        if (f & SW_INIT) s.lists[G + atomicAdd(&n[1], 1)] = g;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) s.lists[2 * G + threadIdx.x] = n[threadIdx.x];
+}
+
 // Harvest bookkeeping + admission, one warp per group (lane = slot). first != 0: start of a chunk, nothing to harvest.
+// A group takes the next 32 frames only once they have arrived (avail); until then it waits with SW_WANT.
 __global__ void __launch_bounds__(256)
 sw2_claim_kernel(SwGroups s, int G, int L, int F, int first, uint32_t load_flags, int32_t *__restrict__ iters_out,
                  uint8_t *__restrict__ ok_out) {
@@ -285,105 +311,114 @@ sw2_claim_kernel(SwGroups s, int G, int L, int F, int first, uint32_t load_flags
     if (g >= G) return;
     const int slot = g * kFG + lane;
     if (!first) {
-        if (!(s.flags[g] & SW_FINAL)) return;
-        const uint32_t v = s.valid[g];
-        if ((v >> lane) & 1u) {
-            const int f = s.frame0[g] + lane;
-            ok_out[f] = (uint8_t)(((s.unsat[g] >> lane) & 1u) ^ 1u);
-            iters_out[f] = s.sum[slot] / L;  // dec.cpp:2193-2194
-        }
-        if (lane == 0) atomicAdd(s.done, (unsigned long long)__popc(v));
+        const uint32_t fl = s.flags[g];
+        if (fl & SW_FINAL) {
+            const uint32_t v = s.valid[g];
+            if ((v >> lane) & 1u) {
+                const int f = s.frame0[g] + lane;
+                ok_out[f] = (uint8_t)(((s.unsat[g] >> lane) & 1u) ^ 1u);
+                iters_out[f] = s.sum[slot] / L;  // dec.cpp:2193-2194
+            }
+            if (lane == 0) atomicAdd(s.done, (unsigned long long)__popc(v));
+        } else if (!(fl & SW_WANT)) return;
     }
-    unsigned long long f0 = 0;
-    if (lane == 0) f0 = atomicAdd(s.next_frame, 32ull);
+    const unsigned long long none = ~0ull;
+    unsigned long long f0 = none, cur = 0;
+    if (lane == 0) {
+        cur = *(volatile unsigned long long *)s.next_frame;
+        const unsigned long long av = *(volatile const unsigned long long *)s.avail;
+        while (cur < av) {
+            const unsigned long long old = atomicCAS(s.next_frame, cur, cur + 32ull);
+            if (old == cur) { f0 = cur; break; }
+            cur = old;
+        }
+    }
     f0 = __shfl_sync(0xffffffffu, f0, 0);
     s.n_pos[slot] = 0;
     s.sum[slot] = 0;
     __syncwarp();  // every lane has read the old frames' state
     if (lane == 0) {
-        if (f0 < (unsigned long long)F) {
+        if (f0 != none) {
             const int left = F - (int)f0;
             const uint32_t v = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
             s.valid[g] = v; s.run[g] = v; s.pos[g] = 0; s.frame0[g] = (int)f0; s.unsat[g] = 0; s.flags[g] = load_flags;
-        } else {
-            s.valid[g] = 0; s.run[g] = 0; s.pos[g] = L; s.flags[g] = 0;
+        } else {  // nothing to take: for good once every frame of the chunk has been claimed
+            s.valid[g] = 0; s.run[g] = 0; s.pos[g] = L; s.flags[g] = cur >= (unsigned long long)F ? 0u : SW_WANT;
         }
     }
 }
 
 // A group's new frames: frame-major staged rows -> slot-interleaved lratio; every decision starts "set" (see sw_load_kernel).
 __global__ void __launch_bounds__(256)
-sw2_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint32_t *__restrict__ decw, SwGroups s, int N) {
-    const int g = blockIdx.y;
-    if (!(s.flags[g] & SW_LOAD)) return;
+sw2_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint32_t *__restrict__ decw, SwGroups s, int N, int G) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j0 = blockIdx.x * 32;
-    const uint32_t v = s.valid[g];
-    const size_t f0 = (size_t)s.frame0[g];
-    for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit
-        const int j = j0 + tx;
-        tile[r][tx] = (((v >> r) & 1u) && j < N) ? in[(f0 + r) * N + j] : 1.0;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {  // r = bit, tx = slot
-        const int j = j0 + r;
-        if (j < N) {
-            lratio[((size_t)g * N + j) * kFG + tx] = tile[tx][r];
-            if (tx == 0) decw[(size_t)g * N + j] = 0xffffffffu;
+    const int n = s.lists[2 * G];
+    for (int a = blockIdx.y; a < n; a += gridDim.y) {
+        const int g = s.lists[a];
+        const uint32_t v = s.valid[g];
+        const size_t f0 = (size_t)s.frame0[g];
+        for (int r = ty; r < 32; r += 8) {  // r = slot, tx = bit
+            const int j = j0 + tx;
+            tile[r][tx] = (((v >> r) & 1u) && j < N) ? in[(f0 + r) * N + j] : 1.0;
         }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {  // r = bit, tx = slot
+            const int j = j0 + r;
+            if (j < N) {
+                lratio[((size_t)g * N + j) * kFG + tx] = tile[tx][r];
+                if (tx == 0) decw[(size_t)g * N + j] = 0xffffffffu;
+            }
+        }
+        __syncthreads();
     }
 }
 
 // alloc_entry's e->pr = e->lr = 0 for a group's new frames (only for window descriptions under which an entry can be
 // read before Init_SW_Decoder has reached its column; the host decides, engine.cu).
 __global__ void __launch_bounds__(256)
-sw2_zero_kernel(double *__restrict__ pr, double *__restrict__ lr, SwGroups s, int E) {
-    const int g = blockIdx.y;
-    if (!(s.flags[g] & SW_ZERO)) return;
+sw2_zero_kernel(double *__restrict__ pr, double *__restrict__ lr, SwGroups s, int E, int G) {
+    const int n = s.lists[2 * G];
     const size_t n2 = (size_t)E * kFG / 2;  // double2 elements per array
-    double2 *a = (double2 *)(pr + (size_t)g * E * kFG), *b = (double2 *)(lr + (size_t)g * E * kFG);
     const double2 z = make_double2(0.0, 0.0);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-        a[i] = z;
-        b[i] = z;
+    for (int a = blockIdx.y; a < n; a += gridDim.y) {
+        const int g = s.lists[a];
+        double2 *pa = (double2 *)(pr + (size_t)g * E * kFG), *pb = (double2 *)(lr + (size_t)g * E * kFG);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+            pa[i] = z;
+            pb[i] = z;
+        }
     }
 }
 
 // Init_SW_Decoder for the columns that enter the window at the group's position.
 __global__ void __launch_bounds__(256)
 sw2_init_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *__restrict__ lratio, SwGroups s,
-                const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N, int E) {
-    const int lane = threadIdx.x & 31, g = blockIdx.y;
-    if (!(s.flags[g] & SW_INIT)) return;
-    const int32_t *r = s.sched + 8 * s.pos[g];
-    const int j = r[6] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= r[7]) return;
-    const double v = lratio[((size_t)g * N + j) * kFG + lane];
-    for (int k = __ldg(col_ptr + j); k < __ldg(col_ptr + j + 1); k++) {
-        const size_t idx = ((size_t)g * E + __ldg(col_edge + k)) * kFG + lane;
-        pr[idx] = v;
-        lr[idx] = 1.0;
+                const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N, int E, int G) {
+    const int lane = threadIdx.x & 31;
+    const int n = s.lists[2 * G + 1];
+    for (int a = blockIdx.y; a < n; a += gridDim.y) {
+        const int g = s.lists[G + a];
+        const int32_t *r = s.sched + 8 * s.pos[g];
+        const int j = r[6] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (j >= r[7]) continue;
+        const double v = lratio[((size_t)g * N + j) * kFG + lane];
+        for (int k = __ldg(col_ptr + j); k < __ldg(col_ptr + j + 1); k++) {
+            const size_t idx = ((size_t)g * E + __ldg(col_edge + k)) * kFG + lane;
+            pr[idx] = v;
+            lr[idx] = 1.0;
+        }
     }
 }
 
-// Check_Update_SW for the checks of the group's window. DC > 0: rows of degree <= DC in registers (sw_row_reg_kernel's
-// arithmetic); DC == 0: the generic loop (sw_row_kernel's).
+// Check_Update_SW for one (check i, slot). DC > 0: rows of degree <= DC in registers (sw_row_reg_kernel's arithmetic);
+// DC == 0: the generic loop (sw_row_kernel's).
 template <int DC>
-__global__ void __launch_bounds__(128)
-sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups s, const int32_t *__restrict__ row_ptr, int E,
-               int max_rows, int G) {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= (long long)G * max_rows) return;
-    const int g = (int)(item / max_rows);
-    const uint32_t run = s.run[g];
-    if (run == 0) return;
-    const int32_t *r = s.sched + 8 * s.pos[g];
-    const int i = r[2] + (int)(item - (long long)g * max_rows);
-    if (i >= r[3] || !((run >> lane) & 1u)) return;
+__device__ __forceinline__ void sw_row_node(const double *__restrict__ pr, double *__restrict__ lr, const int32_t *__restrict__ row_ptr,
+                                            int g, int E, int i, int slot) {
     const int e0 = __ldg(row_ptr + i), deg = __ldg(row_ptr + i + 1) - e0;
-    const double *p = pr + ((size_t)g * E + e0) * kFG + lane;
-    double *l = lr + ((size_t)g * E + e0) * kFG + lane;
+    const double *p = pr + ((size_t)g * E + e0) * kFG + slot;
+    double *l = lr + ((size_t)g * E + e0) * kFG + slot;
     bool bad = DC == 0;
     if (DC > 0) {
         constexpr int D = DC > 0 ? DC : 1;
@@ -423,27 +458,21 @@ sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups 
     }
 }
 
-// Variable_Update_SW + Decision_SW for the bits of the group's window (sw_col_kernel's arithmetic). DV > 0: columns of
-// degree <= DV with every load in flight before the first multiplication (col_row = check of the k-th entry of a
-// column, so that the in-window test needs no dependent lookup): P_k = lratio * lr_0 .. lr_{k-1} over the in-window
-// entries, pr_k = P_k * S_k with S the product from the other end - the values sw_col_kernel leaves in e->pr.
+// Variable_Update_SW + Decision_SW for one (bit j, slot), restricted to the entries whose check lies in [c0, c1)
+// (sw_col_kernel's arithmetic); returns the decision. DV > 0: columns of degree <= DV with every load in flight before
+// the first multiplication (col_row = check of the k-th entry of a column, so that the in-window test needs no
+// dependent lookup): P_k = lratio * lr_0 .. lr_{k-1} over the in-window entries, pr_k = P_k * S_k with S the product
+// from the other end - the values sw_col_kernel leaves in e->pr. `on` = false: no access, decision of a product of 1.
 template <int DV>
-__global__ void __launch_bounds__(256)
-sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
-               uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
-               const int32_t *__restrict__ col_row, int N, int E) {
-    const int lane = threadIdx.x & 31, g = blockIdx.y;
-    const uint32_t run = s.run[g];
-    if (run == 0) return;
-    const int32_t *r = s.sched + 8 * s.pos[g];
-    const int j = r[0] + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= r[1]) return;
-    const int c0 = r[2], c1 = r[3];
-    const bool on = (run >> lane) & 1u;
+__device__ __forceinline__ bool sw_col_node(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
+                                            const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
+                                            const int32_t *__restrict__ col_row, int g, int N, int E, int j, int slot, int c0, int c1,
+                                            bool on) {
+    if (!on) return true;
     const int k0 = __ldg(col_ptr + j), k1 = __ldg(col_ptr + j + 1);
-    double *p = pr + (size_t)g * E * kFG + lane;
-    const double *l = lr + (size_t)g * E * kFG + lane;
-    double acc = on ? lratio[((size_t)g * N + j) * kFG + lane] : 1.0;
+    double *p = pr + (size_t)g * E * kFG + slot;
+    const double *l = lr + (size_t)g * E * kFG + slot;
+    double acc = lratio[((size_t)g * N + j) * kFG + slot];
     if (DV > 0) {
         constexpr int D = DV > 0 ? DV : 1;
         int e[D];
@@ -460,16 +489,11 @@ sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const dou
             }
         }
 #pragma unroll
-        for (int k = 0; k < D; k++) lv[k] = (on && in[k]) ? ld_stream(l + (size_t)e[k] * kFG) : 1.0;
+        for (int k = 0; k < D; k++) lv[k] = in[k] ? ld_stream(l + (size_t)e[k] * kFG) : 1.0;
 #pragma unroll
         for (int k = 0; k < D; k++) {
             P[k] = acc;
             if (in[k]) acc = __dmul_rn(acc, lv[k]);
-        }
-        const uint32_t w = __ballot_sync(0xffffffffu, acc <= 1.0);
-        if (lane == 0) {
-            uint32_t *dst = decw + (size_t)g * N + j;
-            *dst = (w & run) | (*dst & ~run);
         }
         double S = 1.0;
 #pragma unroll
@@ -477,36 +501,92 @@ sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const dou
             if (in[k]) {
                 double v = __dmul_rn(P[k], S);
                 if (v != v) v = 1.0;
-                if (on) st_stream(p + (size_t)e[k] * kFG, v);
+                st_stream(p + (size_t)e[k] * kFG, v);
                 S = __dmul_rn(S, lv[k]);
             }
         }
-        return;
+        return acc <= 1.0;
     }
-    if (on) {
-        for (int k = k0; k < k1; k++) {
-            const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
-            if (row < c1 && row >= c0) {
-                p[(size_t)e * kFG] = acc;
-                acc = __dmul_rn(acc, l[(size_t)e * kFG]);
-            }
+    for (int k = k0; k < k1; k++) {
+        const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+        if (row < c1 && row >= c0) {
+            p[(size_t)e * kFG] = acc;
+            acc = __dmul_rn(acc, l[(size_t)e * kFG]);
         }
     }
-    const uint32_t w = __ballot_sync(0xffffffffu, acc <= 1.0);
-    if (lane == 0) {
-        uint32_t *dst = decw + (size_t)g * N + j;
-        *dst = (w & run) | (*dst & ~run);
+    double sp = 1.0;
+    for (int k = k1 - 1; k >= k0; k--) {
+        const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+        if (row < c1 && row >= c0) {
+            double v = __dmul_rn(p[(size_t)e * kFG], sp);
+            if (v != v) v = 1.0;
+            p[(size_t)e * kFG] = v;
+            sp = __dmul_rn(sp, l[(size_t)e * kFG]);
+        }
     }
-    if (on) {
-        double sp = 1.0;
-        for (int k = k1 - 1; k >= k0; k--) {
-            const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
-            if (row < c1 && row >= c0) {
-                double v = __dmul_rn(p[(size_t)e * kFG], sp);
-                if (v != v) v = 1.0;
-                p[(size_t)e * kFG] = v;
-                sp = __dmul_rn(sp, l[(size_t)e * kFG]);
-            }
+    return acc <= 1.0;
+}
+
+// Lanes a group gives to one node. A group in which only a few frames still iterate at its position (the stragglers that
+// run to max_iter while the others wait) would otherwise spend a whole warp per node on 1-4 useful lanes, and the
+// update kernels, bound by warps in flight, would take as long as for a full group: with n <= 4 / 8 / 16 running frames
+// a warp takes 8 / 4 / 2 nodes at once, lane = (node, k-th running slot).
+__device__ __forceinline__ int sw_lanes_per_node(uint32_t run, int packed) {
+    const int n = __popc(run);
+    return !packed ? 32 : (n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)));
+}
+
+__device__ __forceinline__ int sw_nth_set_bit(uint32_t m, int n) {  // position of the n-th (0-based) set bit, -1 if there are fewer
+    for (int i = 0; i < n; i++) m &= m - 1;
+    return m ? __ffs(m) - 1 : -1;
+}
+
+constexpr int kSwNodesPerCta = 64;  // checks / bits a CTA of 8 warps walks through
+
+template <int DC>
+__global__ void __launch_bounds__(256)
+sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups s, const int32_t *__restrict__ row_ptr, int E,
+               int packed) {
+    const int g = blockIdx.y;
+    const uint32_t run = s.run[g];
+    if (run == 0) return;
+    const int32_t *r = s.sched + 8 * s.pos[g];
+    const int i0 = r[2] + blockIdx.x * kSwNodesPerCta, i1 = min(r[3], i0 + kSwNodesPerCta);
+    if (i0 >= i1) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lpn = sw_lanes_per_node(run, packed), npw = 32 / lpn;
+    const int sub = lane / lpn, k = lane & (lpn - 1);
+    const int slot = lpn == 32 ? lane : sw_nth_set_bit(run, k);  // the k-th running slot, -1 if there are fewer
+    if (slot < 0 || !((run >> slot) & 1u)) return;
+    for (int i = i0 + warp * npw + sub; i < i1; i += 8 * npw) sw_row_node<DC>(pr, lr, row_ptr, g, E, i, slot);
+}
+
+template <int DV>
+__global__ void __launch_bounds__(256)
+sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
+               uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
+               const int32_t *__restrict__ col_row, int N, int E, int packed) {
+    const int g = blockIdx.y;
+    const uint32_t run = s.run[g];
+    if (run == 0) return;
+    const int32_t *r = s.sched + 8 * s.pos[g];
+    const int j0 = r[0] + blockIdx.x * kSwNodesPerCta, j1 = min(r[1], j0 + kSwNodesPerCta);
+    if (j0 >= j1) return;
+    const int c0 = r[2], c1 = r[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lpn = sw_lanes_per_node(run, packed), npw = 32 / lpn;
+    const int sub = lane / lpn, k = lane & (lpn - 1);
+    const int slot = lpn == 32 ? lane : sw_nth_set_bit(run, k);
+    const bool mine = slot >= 0 && ((run >> slot) & 1u);
+    for (int jb = j0 + warp * npw; jb < j1; jb += 8 * npw) {  // warp-uniform trip count: the lanes of a node shuffle below
+        const int j = jb + sub;
+        const bool on = mine && j < j1;
+        const bool bit = sw_col_node<DV>(pr, lr, lratio, col_ptr, col_edge, col_row, g, N, E, j, slot, c0, c1, on);
+        uint32_t w = (on && bit) ? (1u << slot) : 0u;
+        for (int off = 1; off < lpn; off <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, off);  // OR over the node's lanes
+        if (k == 0 && j < j1) {
+            uint32_t *dst = decw + (size_t)g * N + j;
+            *dst = (w & run) | (*dst & ~run);
         }
     }
 }

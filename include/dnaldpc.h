@@ -162,7 +162,7 @@ int dnaldpc_redecode_sweep_ex(dnaldpc_decoder *d, const dnaldpc_input *in, int64
  * iters = floor(sum over positions of Iter_SW_Decoder's n / L) as returned by the reference, is_codeword and pchk from
  * the closing check(). Bits no window has decided yet count as set in the bounded syndromes, as with the reference's
  * dblk buffer pre-filled with 2 (DNA_main.cpp:664-666). The position_BER diagnostic (test_BER) is not produced.
- * fp64 only; runs on the decoder's first device. */
+ * fp64 only. With several devices every device decodes a contiguous share of the frames (no exchange between them). */
 typedef struct dnaldpc_window {
     int32_t code_type, L, w, win;
     const int32_t *Mv, *Mc;

@@ -411,15 +411,16 @@ def test_drain_tail_compaction(code18432, orc18432, cws):
         assert np.array_equal(r["post"][f].view(np.uint64), o["post"].view(np.uint64)), f
 
 
-@pytest.mark.parametrize("switches", [{}, {"DNALDPC_SW_ZERO": "1", "DNALDPC_SW_CHUNK": "32"}, {"DNALDPC_SW_LOCKSTEP": "1"}],
-                         ids=["groups", "groups-zero-chunk32", "lockstep"])
+@pytest.mark.parametrize("switches", [{}, {"DNALDPC_SW_ZERO": "1", "DNALDPC_SW_CHUNK": "64", "DNALDPC_SW_PIECE": "32"},
+                                      {"DNALDPC_SW_LOCKSTEP": "1"}], ids=["groups", "groups-zero-chunk64-piece32", "lockstep"])
 def test_sliding_window_decoder(switches, monkeypatch):
     """sliding-window BP for SC-LDPC codes (dnaldpc_decode_window = Run_SW_Decoder, dec.cpp:2092-2196) on the
     generated (3,6) SC code: (a) the golden vectors produced by the unmodified reference, (b) a ragged batch (frames that
     leave a window position after 0..max_iter extra updates share warp groups; 100 frames through 2 groups of slots)
     against the oracle, for several window sizes incl. win == L (one window over the whole code). Variants: continuous
-    batching by group (the default), the same with every group's message arrays cleared per refill and 32-frame staging
-    chunks (4 chunks), and the wave-lock-step schedule of the first version."""
+    batching by group (the default), the same with every group's message arrays cleared per refill, 64-frame staging
+    chunks and 32-frame copy pieces (groups wait for frames that are still on their way), and the wave-lock-step
+    schedule of the first version."""
     for k, v in switches.items():
         monkeypatch.setenv(k, v)
     g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
@@ -455,6 +456,31 @@ def test_sliding_window_decoder(switches, monkeypatch):
     with pytest.raises(ldpc.LdpcError):  # node counts that do not match the matrix
         dec.decode_window(lr[:2], 5, L, w, 4, Mv * 2, Mc)
     dec.close()
+
+
+def test_sliding_window_multi_device():
+    """dnaldpc_decode_window with several devices: every device decodes a contiguous share of the frames; results equal
+    the one-device decoder's (frames are independent, DNA_main.cpp:629-651)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs more than one GPU")
+    g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
+    code = ldpc.Code(os.path.join(ol.GOLDEN, "sc_z32_l12.pchk"))
+    Mv, Mc, L, w = g["Mv"], g["Mc"], int(g["L"]), int(g["w"])
+    rs = np.random.RandomState(99)
+    F = 64 * ndev + 37
+    eps = rs.choice([0.0, 0.03, 0.05, 0.08], size=F)
+    lr = np.exp(np.where(rs.rand(F, code.N) < eps[:, None], -1.0, 1.0) * rs.uniform(1.0, 4.0, (F, code.N)))
+    one = ldpc.Decoder(code, devices=[0], wave_frames=64)
+    many = ldpc.Decoder(code, devices=list(range(ndev)), wave_frames=64)
+    want = ("bits", "dblk", "iters", "ok", "pchk")
+    a = one.decode_window(lr, 10, L, w, 4, Mv, Mc, want=want)
+    b = many.decode_window(lr, 10, L, w, 4, Mv, Mc, want=want)
+    for k in want:
+        assert np.array_equal(a[k], b[k]), k
+    assert len(set(a["iters"].tolist())) > 2
+    one.close(); many.close()
 
 
 def test_compaction_stress_small_code():

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=20)
     ap.add_argument("--wave", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--warm", type=int, default=0, help="frames of the warm-up call (default: one wave)")
     a = ap.parse_args()
     ldpc = _pkg.load()
     M, N, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(a.z, a.L, 11)
@@ -55,13 +56,21 @@ def main():
         rc = ldpc.lib().dnaldpc_decode_window(dec._h, C.byref(wd), lr.data_ptr(), nf, a.max_iter, C.byref(out))
         if rc:
             raise RuntimeError(ldpc.lib().dnaldpc_last_error())
-    call(min(a.frames, a.wave))  # warm-up: slot arrays, staging buffers
+    call(min(a.frames, a.warm or a.wave))  # warm-up: slot arrays, staging buffers
     dts = []
     for _ in range(a.reps):
         t0 = time.perf_counter()
         call(a.frames)
         dts.append(time.perf_counter() - t0)
     dt = min(dts)
+    # the input copy alone (pinned host -> device), for comparison: the call cannot be faster than this
+    dev_buf = torch.empty_like(lr, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_buf.copy_(lr, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = time.perf_counter() - t0
+    del dev_buf
     st = dec.stats()
     r = {"iters": iters.numpy(), "ok": okf.numpy(),
          "bits": np.unpackbits(bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :N]}
@@ -74,7 +83,8 @@ def main():
            "fer": 1.0 - float((r["ok"] == 1).mean()), "bit_errors": int(r["bits"].sum()),
            "avg_updates_per_position": upd / a.frames / a.L, "kernel_launches": st["kernel_launches"], "ticks": st["waves"], "wave_frames": a.wave,
            "schedule": "lock-step" if os.environ.get("DNALDPC_SW_LOCKSTEP", "0") not in ("", "0") else "groups",
-           "algorithmic_gb_s": upd * bytes_upd / dt / 1e9}
+           "algorithmic_gb_s": upd * bytes_upd / dt / 1e9,
+           "input_bytes": int(lr.numel()) * 8, "input_copy_alone_s": h2d_s, "input_copy_alone_gb_s": int(lr.numel()) * 8 / h2d_s / 1e9}
     print(json.dumps(out))
 
 
