@@ -238,7 +238,51 @@ def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
         out["c5_n65536_eps%g_%d" % (eps5, F5)] = run_device(dec5, ldpc.IN_BSC_BITS, d_in, F5, eps5, 50, n5, b_iter=b5)
         del d_in
     dec5.close()
+    out["sw_z1024_l24_eps0.03_8192"] = sliding_window_leg(ldpc, torch, args)
     return out
+
+
+def sliding_window_leg(ldpc, torch, args, Z=1024, Lc=24, win=6, F=8192, eps=0.03, max_iter=20):
+    """dnaldpc_decode_window (Run_SW_Decoder, dec.cpp:2092-2196) on a terminated (3,6) SC-LDPC code from tools/gen_sc_pchk.py:
+    all-zero codeword through a BSC, fp64 ratios in pinned host memory, host buffers out; the C-ABI call alone is timed."""
+    import gen_sc_pchk
+    Cc = ldpc.C
+    Ms, Ns, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(Z, Lc, 11)
+    code = ldpc.Code(csr=(Ms, Ns, row_ptr, col_idx))
+    dec = ldpc.Decoder(code, devices=[torch.cuda.current_device()], wave_frames=args.wave)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device=dev); gen.manual_seed(args.seed)
+    h_lr = torch.empty((F, Ns), dtype=torch.float64).pin_memory()
+    for f0 in range(0, F, 1024):  # ratios made on the device in slices, parked in pinned host memory
+        fl = torch.rand((min(1024, F - f0), Ns), device=dev, generator=gen) < eps
+        h_lr[f0:f0 + fl.shape[0]].copy_(torch.where(fl, eps / (1 - eps), (1 - eps) / eps).to(torch.float64))
+    D = Lc + 3 - 1
+    mv = np.ascontiguousarray(Mv[:D], dtype=np.int32); mc = np.ascontiguousarray(Mc[:D], dtype=np.int32)
+    Ws = (Ns + 31) // 32
+    h_bits = torch.zeros((F, Ws), dtype=torch.int32).pin_memory()
+    h_it = torch.zeros(F, dtype=torch.int32).pin_memory()
+    h_ok = torch.zeros(F, dtype=torch.uint8).pin_memory()
+    wd = ldpc.Window(code_type=0, L=Lc, w=3, win=win, Mv=mv.ctypes.data, Mc=mc.ctypes.data)
+    outp = ldpc.Output(bits=h_bits.data_ptr(), dblk=None, iters=h_it.data_ptr(), is_codeword=h_ok.data_ptr(), posterior=None, pchk=None)
+
+    def go(nf):
+        rc = ldpc.lib().dnaldpc_decode_window(dec._h, Cc.byref(wd), h_lr.data_ptr(), nf, max_iter, Cc.byref(outp))
+        if rc:
+            raise RuntimeError(ldpc.lib().dnaldpc_last_error())
+    go(min(F, args.wave))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    go(F)
+    dt = time.perf_counter() - t0
+    stt = dec.stats()
+    ok = h_ok.numpy()
+    good = torch.from_numpy(ok.astype(bool))
+    r = {"frames": F, "ms": dt * 1e3, "gbit_s": F * Ns / dt / 1e9, "frames_per_s": F / dt, "fer": 1.0 - float(ok.mean()),
+         "code": {"Z": Z, "L": Lc, "N": Ns, "M": Ms, "window": win}, "max_extra_updates": max_iter, "ticks": stt["waves"],
+         "kernel_launches": stt["kernel_launches"], "h2d_bytes": F * Ns * 8, "d2h_bytes": F * (Ws * 4 + 5),
+         "flagged_frames_are_the_sent_codeword": bool((h_bits[good] == 0).all().item()) if ok.any() else True}
+    dec.close()
+    return r
 
 
 def host_leg(ldpc, torch, dec, kind, h_in, F, param, max_iter, device_ref, flags=0):
