@@ -80,7 +80,7 @@ Engine::~Engine() {
     cudaDeviceSynchronize();
     void *ptrs[] = {d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_msg_, d_lratio_, d_post_, d_decw_, d_masks_, d_arrive_,
                     d_slot_, d_mv_, d_sw_lr_, d_edge_row_, d_next_, d_iters_, d_ok_, d_table_, d_counters_, s_in_, s_bits_, s_dblk_, s_post_, s_pchk_,
-                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1], d_col_row_, d_sw_sched_, s_in2_, d_sw_avail_, d_sw_lists_};
+                    s_iters_, s_ok_, d_rows_, d_synth_thr_, d_list_[0], d_list_[1], d_col_row_, d_sw_sched_, s_in2_, d_sw_avail_, d_sw_lists_, d_sw_thin_, d_sw_hist_};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_bounce_) cudaFreeHost(h_bounce_);
@@ -714,8 +714,21 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
     if (G > sw_cap_lists_) {
         if (d_sw_lists_) cudaFree(d_sw_lists_);
         d_sw_lists_ = nullptr; sw_cap_lists_ = 0;
-        CK(cudaMalloc((void **)&d_sw_lists_, ((size_t)2 * G + 2) * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&d_sw_lists_, ((size_t)7 * G + 4) * sizeof(int32_t)));  // 4 lists + 4 counts, then thin_map / thin_e0 / thin_ne
         sw_cap_lists_ = G;
+    }
+    // straggler mode (sw2_thin_copy_kernel): side arrays with 4 slots per edge for the edges of one window's checks
+    int thin_edges = 0;
+    for (int t = 0; t < L; t++) thin_edges = std::max(thin_edges, code.row_ptr[sched[(size_t)8 * t + 3]] - code.row_ptr[sched[(size_t)8 * t + 2]]);
+    const bool thin_on = !(getenv("DNALDPC_SW_THIN") && atoi(getenv("DNALDPC_SW_THIN")) == 0) && thin_edges > 0;  // A/B switch
+    if (thin_on) {
+        const size_t need = (size_t)G * thin_edges * kSwThinLanes * 2 * sizeof(double);
+        if (need > sw_cap_thin_) {
+            if (d_sw_thin_) cudaFree(d_sw_thin_);
+            d_sw_thin_ = nullptr; sw_cap_thin_ = 0;
+            CK(cudaMalloc(&d_sw_thin_, need));
+            sw_cap_thin_ = need;
+        }
     }
     // A chunk is copied in pieces of about 64 MB; behind every piece the copy stream publishes how many frames of the
     // chunk are resident, and the groups only take frames that are (sw2_claim_kernel): decoding starts with the first
@@ -758,6 +771,18 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
         const double *in = (const double *)*in_buf[b];
         s.avail = d_sw_avail_ + b;
         s.lists = d_sw_lists_;
+        s.thin_map = (uint32_t *)(d_sw_lists_ + 4 * (size_t)sw_cap_lists_ + 4);
+        s.thin_e0 = d_sw_lists_ + 5 * (size_t)sw_cap_lists_ + 4;
+        s.thin_ne = d_sw_lists_ + 6 * (size_t)sw_cap_lists_ + 4;
+        s.thin_edges = thin_edges;
+        s.hist = nullptr;
+        if (getenv("DNALDPC_SW_HIST")) {  // diagnostics: how many frames of a group run in an update
+            if (!d_sw_hist_) CK(cudaMalloc((void **)&d_sw_hist_, 66 * sizeof(unsigned long long)));
+            CK(cudaMemsetAsync(d_sw_hist_, 0, 66 * sizeof(unsigned long long), st));
+            s.hist = d_sw_hist_;
+        }
+        s.thin_pr = thin_on ? (double *)d_sw_thin_ : nullptr;
+        s.thin_lr = thin_on ? (double *)d_sw_thin_ + (size_t)G * thin_edges * kSwThinLanes : nullptr;
         CK(cudaMemsetAsync(d_next_, 0, 3 * sizeof(unsigned long long), st));
         const unsigned claim_grid = (unsigned)((Gc * kFG + 255) / 256);
         sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 1, load_flags, d_iters_, d_ok_);
@@ -768,7 +793,9 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
             sw2_list_kernel<<<1, 1024, 0, st>>>(s, Gc);
             sw2_load_kernel<<<dim3(load_x, head_y), 256, 0, st>>>(in, lrat, d_decw_, s, N_, Gc);
             if (zero) sw2_zero_kernel<<<dim3(64, head_y), 256, 0, st>>>(pr, lr, s, E_, Gc);
+            if (thin_on) sw2_thin_copy_kernel<<<dim3(32, head_y), 256, 0, st>>>(pr, s, E_, Gc, 1);  // back, before Init_SW_Decoder of the new position
             if (max_init > 0) sw2_init_kernel<<<dim3((unsigned)((max_init + 7) / 8), head_y), 256, 0, st>>>(pr, lr, lrat, s, d_col_ptr_, d_col_edge_, N_, E_, Gc);
+            if (thin_on) sw2_thin_copy_kernel<<<dim3(32, head_y), 256, 0, st>>>(pr, s, E_, Gc, 0);
             if (max_rows > 0) {
                 const dim3 grid((unsigned)((max_rows + kSwNodesPerCta - 1) / kSwNodesPerCta), (unsigned)Gc);
                 if (max_row_deg_ <= 8) sw2_row_kernel<8><<<grid, 256, 0, st>>>(pr, lr, s, d_row_ptr_, E_, packed);
@@ -784,7 +811,7 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
             sw2_final_syn_kernel<<<dim3(kSwFinalSplit, (unsigned)Gc), 256, 0, st>>>(d_decw_, s, d_row_ptr_, d_col_idx_, N_, M_, o.pchk);
             if (o.bits || o.dblk) sw2_output_kernel<<<dim3((unsigned)((wpf + 7) / 8), (unsigned)Gc), 256, 0, st>>>(d_decw_, s, N_, (int)wpf, o.bits, o.dblk);
             sw2_claim_kernel<<<claim_grid, 256, 0, st>>>(s, Gc, L, nf, 0, load_flags, d_iters_, d_ok_);
-            stats.kernel_launches += 10;
+            stats.kernel_launches += thin_on ? 12 : 10;
             stats.waves++;  // ticks
             unsigned *hc = h_counters_ + kCounterWords * (tick % kRing);
             CK(cudaMemcpyAsync(hc, d_next_ + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -804,6 +831,15 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
         if (out.iters) CK(cudaMemcpyAsync(out.iters + f0, d_iters_, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
         if (out.is_codeword) CK(cudaMemcpyAsync(out.is_codeword + f0, d_ok_, (size_t)nf, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (s.hist) {
+            unsigned long long h[66];
+            CK(cudaMemcpy(h, d_sw_hist_, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "sw group-updates by running frames (chunk at frame %lld):", (long long)f0);
+            for (int k = 1; k <= 32; k++) fprintf(stderr, " %d:%llu", k, h[k]);
+            fprintf(stderr, "\n  of which in straggler mode:");
+            for (int k = 1; k <= 4; k++) fprintf(stderr, " %d:%llu", k, h[33 + k]);
+            fprintf(stderr, "\n");
+        }
     }
     if (out.iters) for (int64_t f = 0; f < F; f++) stats.frame_iters += out.iters[f];
     return DNALDPC_OK;

@@ -118,8 +118,11 @@ class Engine {
     int32_t *d_sw_sched_ = nullptr;                      // sliding-window mode: window ranges per position [L][8]
     int sw_cap_sched_ = 0;
     unsigned long long *d_sw_avail_ = nullptr;           // sliding-window mode: frames resident per input buffer [2]
-    int32_t *d_sw_lists_ = nullptr;                      // sliding-window mode: per-tick work lists [2][G] + 2 counts
+    int32_t *d_sw_lists_ = nullptr;                      // sliding-window mode: per-tick work lists [4][G] + 4 counts, straggler tables [3][G]
     int sw_cap_lists_ = 0;
+    void *d_sw_thin_ = nullptr;                          // sliding-window mode: straggler side arrays [2][G][edges][4]
+    size_t sw_cap_thin_ = 0;
+    unsigned long long *d_sw_hist_ = nullptr;            // sliding-window mode: diagnostics (DNALDPC_SW_HIST)
     cudaEvent_t sw_in_ev_[2] = {nullptr, nullptr};       // sliding-window mode: a chunk's inputs have arrived
     int32_t *d_mv_ = nullptr;                            // drain-tail compaction: src[S], dst[S], {count, K}
     // compact when busy slots <= 15/16 of the packed region: a move is cheap next to the ticks it shortens (measured

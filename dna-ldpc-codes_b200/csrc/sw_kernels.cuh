@@ -263,6 +263,11 @@ sw_syn_kernel(const uint32_t *__restrict__ decw, uint32_t *__restrict__ runw, in
 // finished frames, a few ticks late. Per (check, frame) and (bit, frame) the arithmetic is that of the kernels above.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t SW_LOAD = 1u, SW_INIT = 2u, SW_FINAL = 4u, SW_ZERO = 8u, SW_WANT = 16u;
+// Straggler mode of a group (see sw2_thin_in_kernel): SW_THIN while the group's few running frames iterate in the compact
+// side arrays, SW_THIN_IN / SW_THIN_OUT = copy their bit->check messages in / back at the head of the next tick.
+constexpr uint32_t SW_THIN = 32u, SW_THIN_IN = 64u, SW_THIN_OUT = 128u;
+constexpr int kSwThinLanes = 4;     // frames a group can take into straggler mode = doubles per 32-byte sector
+constexpr int kSwThinMinLeft = 3;   // ... if they may still run at least this many updates at the position
 
 struct SwGroups {
     int32_t *pos;        // [G] window position of the group, L = no frames
@@ -277,7 +282,13 @@ struct SwGroups {
     const int32_t *sched;  // [L*8] window ranges per position (engine.cu:sw_schedule)
     unsigned long long *next_frame, *done;  // claim counter, frames harvested
     const unsigned long long *avail;        // frames of the chunk that have arrived in HBM (sw2_publish_kernel)
-    int32_t *lists;      // [2][G] groups flagged SW_LOAD / SW_INIT in this tick, [2G], [2G+1] their counts (sw2_list_kernel)
+    int32_t *lists;      // [4][G] groups flagged SW_LOAD / SW_INIT / SW_THIN_IN / SW_THIN_OUT in this tick, then the 4 counts
+    // straggler mode (thin_pr == nullptr: switched off)
+    double *thin_pr, *thin_lr;  // [G][thin_edges][4]: messages of the window's checks for the group's <= 4 stragglers
+    uint32_t *thin_map;         // [G] byte k = slot of straggler k, 0xff = none
+    int32_t *thin_e0, *thin_ne; // [G] first edge / number of edges of the window's checks when the group went thin
+    int thin_edges;             // edges the side arrays hold per group (most edges of any window's checks)
+    unsigned long long *hist;   // diagnostics (DNALDPC_SW_HIST=1), else nullptr: [0..32] group-updates by running frames, [33..65] the same in straggler mode
 };
 
 // The copy stream says how many frames of the chunk are resident (ordered behind the copy that brought them).
@@ -290,18 +301,45 @@ __global__ void sw2_publish_kernel(unsigned long long *avail, unsigned long long
 // walk these instead of launching a CTA per (group, tile) that finds nothing to do).
 __global__ void __launch_bounds__(1024)
 sw2_list_kernel(SwGroups s, int G) {
-    __shared__ int n[2];
-    if (threadIdx.x < 2) n[threadIdx.x] = 0;
+    __shared__ int n[4];
+    if (threadIdx.x < 4) n[threadIdx.x] = 0;
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         const uint32_t f = s.flags[g];
         if (f & SW_LOAD) s.lists[atomicAdd(&n[0], 1)] = g;
         if (f & SW_INIT) s.lists[G + atomicAdd(&n[1], 1)] = g;
+        if (f & SW_THIN_IN) s.lists[2 * G + atomicAdd(&n[2], 1)] = g;
+        if (f & SW_THIN_OUT) s.lists[3 * G + atomicAdd(&n[3], 1)] = g;
     }
     __syncthreads();
-    if (threadIdx.x < 2) s.lists[2 * G + threadIdx.x] = n[threadIdx.x];
+    if (threadIdx.x < 4) s.lists[4 * G + threadIdx.x] = n[threadIdx.x];
 }
 
+// Straggler mode. Once a position's quick frames are done, a group's 1-4 frames that iterate on (typically to max_iter)
+// would move a 32-byte sector per 8-byte message, next to the values of the waiting frames. Their messages of the
+// window's checks (a contiguous edge range in CSR order; every entry the window's updates touch) are therefore copied
+// into side arrays with FOUR slots per edge - one sector - and the updates of the position's remaining iterations run
+// there; when the position is done the bit->check messages are copied back (the check->bit ones are rewritten by the
+// next update before anything reads them). dir = 0: in (list 2), 1: out (list 3).
+__global__ void __launch_bounds__(256)
+sw2_thin_copy_kernel(double *__restrict__ pr, SwGroups s, int E, int G, int dir) {
+    const int n = s.lists[4 * G + 2 + dir];
+    for (int a = blockIdx.y; a < n; a += gridDim.y) {
+        const int g = s.lists[(2 + dir) * G + a];
+        const uint32_t map = s.thin_map[g];
+        const int e0 = s.thin_e0[g], ne = s.thin_ne[g];
+        double *main_g = pr + ((size_t)g * E + e0) * kFG;
+        double *thin_g = s.thin_pr + (size_t)g * s.thin_edges * kSwThinLanes;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ne * kSwThinLanes; idx += gridDim.x * blockDim.x) {
+            const int e = idx >> 2, k = idx & 3;
+            const uint32_t slot = (map >> (8 * k)) & 0xffu;
+            if (slot < 32u) {
+                if (dir == 0) thin_g[idx] = main_g[(size_t)e * kFG + slot];
+                else main_g[(size_t)e * kFG + slot] = thin_g[idx];
+            } else if (dir == 0) thin_g[idx] = 1.0;
+        }
+    }
+}
 // Harvest bookkeeping + admission, one warp per group (lane = slot). first != 0: start of a chunk, nothing to harvest.
 // A group takes the next 32 frames only once they have arrived (avail); until then it waits with SW_WANT.
 __global__ void __launch_bounds__(256)
@@ -353,7 +391,7 @@ __global__ void __launch_bounds__(256)
 sw2_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint32_t *__restrict__ decw, SwGroups s, int N, int G) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j0 = blockIdx.x * 32;
-    const int n = s.lists[2 * G];
+    const int n = s.lists[4 * G];
     for (int a = blockIdx.y; a < n; a += gridDim.y) {
         const int g = s.lists[a];
         const uint32_t v = s.valid[g];
@@ -378,7 +416,7 @@ sw2_load_kernel(const double *__restrict__ in, double *__restrict__ lratio, uint
 // read before Init_SW_Decoder has reached its column; the host decides, engine.cu).
 __global__ void __launch_bounds__(256)
 sw2_zero_kernel(double *__restrict__ pr, double *__restrict__ lr, SwGroups s, int E, int G) {
-    const int n = s.lists[2 * G];
+    const int n = s.lists[4 * G];
     const size_t n2 = (size_t)E * kFG / 2;  // double2 elements per array
     const double2 z = make_double2(0.0, 0.0);
     for (int a = blockIdx.y; a < n; a += gridDim.y) {
@@ -396,7 +434,7 @@ __global__ void __launch_bounds__(256)
 sw2_init_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *__restrict__ lratio, SwGroups s,
                 const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge, int N, int E, int G) {
     const int lane = threadIdx.x & 31;
-    const int n = s.lists[2 * G + 1];
+    const int n = s.lists[4 * G + 1];
     for (int a = blockIdx.y; a < n; a += gridDim.y) {
         const int g = s.lists[G + a];
         const int32_t *r = s.sched + 8 * s.pos[g];
@@ -411,20 +449,17 @@ sw2_init_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *
     }
 }
 
-// Check_Update_SW for one (check i, slot). DC > 0: rows of degree <= DC in registers (sw_row_reg_kernel's arithmetic);
-// DC == 0: the generic loop (sw_row_kernel's).
+// Check_Update_SW for one (check, slot): p / l point at the row's first bit->check / check->bit message of the slot,
+// consecutive entries `stride` doubles apart. DC > 0: rows of degree <= DC in registers (sw_row_reg_kernel's
+// arithmetic); DC == 0: the generic loop (sw_row_kernel's).
 template <int DC>
-__device__ __forceinline__ void sw_row_node(const double *__restrict__ pr, double *__restrict__ lr, const int32_t *__restrict__ row_ptr,
-                                            int g, int E, int i, int slot) {
-    const int e0 = __ldg(row_ptr + i), deg = __ldg(row_ptr + i + 1) - e0;
-    const double *p = pr + ((size_t)g * E + e0) * kFG + slot;
-    double *l = lr + ((size_t)g * E + e0) * kFG + slot;
+__device__ __forceinline__ void sw_row_node(const double *__restrict__ p, double *__restrict__ l, int deg, int stride) {
     bool bad = DC == 0;
     if (DC > 0) {
         constexpr int D = DC > 0 ? DC : 1;
         double d[D], Bv[D];
 #pragma unroll
-        for (int k = 0; k < D; k++) d[k] = k < deg ? ld_stream(p + (size_t)k * kFG) : 0.0;
+        for (int k = 0; k < D; k++) d[k] = k < deg ? ld_stream(p + (size_t)k * stride) : 0.0;
 #pragma unroll
         for (int k = 0; k < D; k++) d[k] = k < deg ? check_factor(d[k], bad) : 1.0;  // padding: exact identity in both chains
         if (!bad) {
@@ -438,7 +473,7 @@ __device__ __forceinline__ void sw_row_node(const double *__restrict__ pr, doubl
 #pragma unroll
             for (int k = 0; k < D; k++) {
                 const double t = __dmul_rn(F, Bv[k]);
-                if (k < deg) st_stream(l + (size_t)k * kFG, check_to_bit(t));
+                if (k < deg) st_stream(l + (size_t)k * stride, check_to_bit(t));
                 F = __dmul_rn(F, d[k]);
             }
         }
@@ -446,33 +481,32 @@ __device__ __forceinline__ void sw_row_node(const double *__restrict__ pr, doubl
     if (bad) {  // generic rows, or operands outside the proven ranges: the full-range loop of sw_row_kernel
         double dl = 1.0;
         for (int k = 0; k < deg; k++) {
-            l[(size_t)k * kFG] = dl;
-            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+            l[(size_t)k * stride] = dl;
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * stride]));
         }
         dl = 1.0;
         for (int k = deg - 1; k >= 0; k--) {
-            const double t = __dmul_rn(l[(size_t)k * kFG], dl);
-            l[(size_t)k * kFG] = check_to_bit_slow(t);
-            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * kFG]));
+            const double t = __dmul_rn(l[(size_t)k * stride], dl);
+            l[(size_t)k * stride] = check_to_bit_slow(t);
+            dl = __dmul_rn(dl, check_factor_slow(p[(size_t)k * stride]));
         }
     }
 }
 
 // Variable_Update_SW + Decision_SW for one (bit j, slot), restricted to the entries whose check lies in [c0, c1)
-// (sw_col_kernel's arithmetic); returns the decision. DV > 0: columns of degree <= DV with every load in flight before
-// the first multiplication (col_row = check of the k-th entry of a column, so that the in-window test needs no
-// dependent lookup): P_k = lratio * lr_0 .. lr_{k-1} over the in-window entries, pr_k = P_k * S_k with S the product
-// from the other end - the values sw_col_kernel leaves in e->pr. `on` = false: no access, decision of a product of 1.
+// (sw_col_kernel's arithmetic); returns the decision. p / l: the slot's message of edge `ebase`, consecutive edges
+// `stride` doubles apart; lrat: the slot's channel ratio of bit j. DV > 0: columns of degree <= DV with every load in
+// flight before the first multiplication (col_row = check of the k-th entry of a column, so that the in-window test
+// needs no dependent lookup): P_k = lratio * lr_0 .. lr_{k-1} over the in-window entries, pr_k = P_k * S_k with S the
+// product from the other end - the values sw_col_kernel leaves in e->pr. `on` = false: no access at all.
 template <int DV>
-__device__ __forceinline__ bool sw_col_node(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
-                                            const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
-                                            const int32_t *__restrict__ col_row, int g, int N, int E, int j, int slot, int c0, int c1,
-                                            bool on) {
+__device__ __forceinline__ bool sw_col_node(double *__restrict__ p, const double *__restrict__ l, int stride, int ebase,
+                                            const double *__restrict__ lrat, const int32_t *__restrict__ col_ptr,
+                                            const int32_t *__restrict__ col_edge, const int32_t *__restrict__ col_row, int j, int c0,
+                                            int c1, bool on) {
     if (!on) return true;
     const int k0 = __ldg(col_ptr + j), k1 = __ldg(col_ptr + j + 1);
-    double *p = pr + (size_t)g * E * kFG + slot;
-    const double *l = lr + (size_t)g * E * kFG + slot;
-    double acc = lratio[((size_t)g * N + j) * kFG + slot];
+    double acc = *lrat;
     if (DV > 0) {
         constexpr int D = DV > 0 ? DV : 1;
         int e[D];
@@ -484,12 +518,12 @@ __device__ __forceinline__ bool sw_col_node(double *__restrict__ pr, const doubl
             e[k] = 0;
             if (k0 + k < k1) {
                 const int row = __ldg(col_row + k0 + k);
-                e[k] = __ldg(col_edge + k0 + k);
                 in[k] = row < c1 && row >= c0;
+                if (in[k]) e[k] = __ldg(col_edge + k0 + k) - ebase;
             }
         }
 #pragma unroll
-        for (int k = 0; k < D; k++) lv[k] = in[k] ? ld_stream(l + (size_t)e[k] * kFG) : 1.0;
+        for (int k = 0; k < D; k++) lv[k] = in[k] ? ld_stream(l + (size_t)e[k] * stride) : 1.0;
 #pragma unroll
         for (int k = 0; k < D; k++) {
             P[k] = acc;
@@ -501,27 +535,29 @@ __device__ __forceinline__ bool sw_col_node(double *__restrict__ pr, const doubl
             if (in[k]) {
                 double v = __dmul_rn(P[k], S);
                 if (v != v) v = 1.0;
-                st_stream(p + (size_t)e[k] * kFG, v);
+                st_stream(p + (size_t)e[k] * stride, v);
                 S = __dmul_rn(S, lv[k]);
             }
         }
         return acc <= 1.0;
     }
     for (int k = k0; k < k1; k++) {
-        const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+        const int row = __ldg(col_row + k);
         if (row < c1 && row >= c0) {
-            p[(size_t)e * kFG] = acc;
-            acc = __dmul_rn(acc, l[(size_t)e * kFG]);
+            const size_t o = (size_t)(__ldg(col_edge + k) - ebase) * stride;
+            p[o] = acc;
+            acc = __dmul_rn(acc, l[o]);
         }
     }
     double sp = 1.0;
     for (int k = k1 - 1; k >= k0; k--) {
-        const int e = __ldg(col_edge + k), row = __ldg(col_row + k);
+        const int row = __ldg(col_row + k);
         if (row < c1 && row >= c0) {
-            double v = __dmul_rn(p[(size_t)e * kFG], sp);
+            const size_t o = (size_t)(__ldg(col_edge + k) - ebase) * stride;
+            double v = __dmul_rn(p[o], sp);
             if (v != v) v = 1.0;
-            p[(size_t)e * kFG] = v;
-            sp = __dmul_rn(sp, l[(size_t)e * kFG]);
+            p[o] = v;
+            sp = __dmul_rn(sp, l[o]);
         }
     }
     return acc <= 1.0;
@@ -543,9 +579,41 @@ __device__ __forceinline__ int sw_nth_set_bit(uint32_t m, int n) {  // position 
 
 constexpr int kSwNodesPerCta = 64;  // checks / bits a CTA of 8 warps walks through
 
+// Which slot a lane works for and where its messages live: the group's slot-interleaved arrays (stride 32, edge 0 of
+// the matrix) or, in straggler mode, the side arrays (stride 4, first edge of the window's checks).
+struct SwLane {
+    int lpn, slot;     // lanes per node; slot = -1: nothing to do
+    int stride, ebase;
+    double *pr, *lr;   // the slot's message of edge `ebase`
+};
+__device__ __forceinline__ SwLane sw_lane_setup(const SwGroups &s, double *pr, double *lr, int g, int E, uint32_t run, int lane, int packed) {
+    SwLane L;
+    if (s.flags[g] & SW_THIN) {
+        const int k = lane & (kSwThinLanes - 1);
+        const uint32_t sl = (s.thin_map[g] >> (8 * k)) & 0xffu;
+        L.lpn = kSwThinLanes;
+        L.slot = (sl < 32u && ((run >> sl) & 1u)) ? (int)sl : -1;
+        L.stride = kSwThinLanes;
+        L.ebase = s.thin_e0[g];
+        const size_t o = (size_t)g * s.thin_edges * kSwThinLanes + k;
+        L.pr = s.thin_pr + o;
+        L.lr = s.thin_lr + o;
+        return L;
+    }
+    L.lpn = sw_lanes_per_node(run, packed);
+    const int sl = L.lpn == 32 ? lane : sw_nth_set_bit(run, lane & (L.lpn - 1));
+    L.slot = (sl >= 0 && ((run >> sl) & 1u)) ? sl : -1;
+    L.stride = kFG;
+    L.ebase = 0;
+    const size_t o = (size_t)g * E * kFG + (sl >= 0 ? sl : 0);
+    L.pr = pr + o;
+    L.lr = lr + o;
+    return L;
+}
+
 template <int DC>
 __global__ void __launch_bounds__(256)
-sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups s, const int32_t *__restrict__ row_ptr, int E,
+sw2_row_kernel(double *__restrict__ pr, double *__restrict__ lr, SwGroups s, const int32_t *__restrict__ row_ptr, int E,
                int packed) {
     const int g = blockIdx.y;
     const uint32_t run = s.run[g];
@@ -554,16 +622,19 @@ sw2_row_kernel(const double *__restrict__ pr, double *__restrict__ lr, SwGroups 
     const int i0 = r[2] + blockIdx.x * kSwNodesPerCta, i1 = min(r[3], i0 + kSwNodesPerCta);
     if (i0 >= i1) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lpn = sw_lanes_per_node(run, packed), npw = 32 / lpn;
-    const int sub = lane / lpn, k = lane & (lpn - 1);
-    const int slot = lpn == 32 ? lane : sw_nth_set_bit(run, k);  // the k-th running slot, -1 if there are fewer
-    if (slot < 0 || !((run >> slot) & 1u)) return;
-    for (int i = i0 + warp * npw + sub; i < i1; i += 8 * npw) sw_row_node<DC>(pr, lr, row_ptr, g, E, i, slot);
+    const SwLane L = sw_lane_setup(s, pr, lr, g, E, run, lane, packed);
+    if (L.slot < 0) return;
+    const int npw = 32 / L.lpn, sub = lane / L.lpn;
+    for (int i = i0 + warp * npw + sub; i < i1; i += 8 * npw) {
+        const int e0 = __ldg(row_ptr + i), deg = __ldg(row_ptr + i + 1) - e0;
+        const size_t o = (size_t)(e0 - L.ebase) * L.stride;
+        sw_row_node<DC>(L.pr + o, L.lr + o, deg, L.stride);
+    }
 }
 
 template <int DV>
 __global__ void __launch_bounds__(256)
-sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const double *__restrict__ lratio,
+sw2_col_kernel(double *__restrict__ pr, double *__restrict__ lr, const double *__restrict__ lratio,
                uint32_t *__restrict__ decw, SwGroups s, const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ col_edge,
                const int32_t *__restrict__ col_row, int N, int E, int packed) {
     const int g = blockIdx.y;
@@ -574,16 +645,15 @@ sw2_col_kernel(double *__restrict__ pr, const double *__restrict__ lr, const dou
     if (j0 >= j1) return;
     const int c0 = r[2], c1 = r[3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lpn = sw_lanes_per_node(run, packed), npw = 32 / lpn;
-    const int sub = lane / lpn, k = lane & (lpn - 1);
-    const int slot = lpn == 32 ? lane : sw_nth_set_bit(run, k);
-    const bool mine = slot >= 0 && ((run >> slot) & 1u);
+    const SwLane L = sw_lane_setup(s, pr, lr, g, E, run, lane, packed);
+    const int npw = 32 / L.lpn, sub = lane / L.lpn, k = lane & (L.lpn - 1);
+    const double *lrat = lratio + (size_t)g * N * kFG + (L.slot >= 0 ? L.slot : 0);
     for (int jb = j0 + warp * npw; jb < j1; jb += 8 * npw) {  // warp-uniform trip count: the lanes of a node shuffle below
         const int j = jb + sub;
-        const bool on = mine && j < j1;
-        const bool bit = sw_col_node<DV>(pr, lr, lratio, col_ptr, col_edge, col_row, g, N, E, j, slot, c0, c1, on);
-        uint32_t w = (on && bit) ? (1u << slot) : 0u;
-        for (int off = 1; off < lpn; off <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, off);  // OR over the node's lanes
+        const bool on = L.slot >= 0 && j < j1;
+        const bool bit = sw_col_node<DV>(L.pr, L.lr, L.stride, L.ebase, lrat + (size_t)j * kFG, col_ptr, col_edge, col_row, j, c0, c1, on);
+        uint32_t w = (on && bit) ? (1u << L.slot) : 0u;
+        for (int off = 1; off < L.lpn; off <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, off);  // OR over the node's lanes
         if (k == 0 && j < j1) {
             uint32_t *dst = decw + (size_t)g * N + j;
             *dst = (w & run) | (*dst & ~run);
@@ -602,6 +672,7 @@ sw2_syn_kernel(const uint32_t *__restrict__ decw, SwGroups s, const int32_t *__r
     const int t = s.pos[g];
     const int32_t *r = s.sched + 8 * t;
     const int v0 = r[0], vc = r[4], c0 = r[2], cc = r[5];
+    if (s.hist != nullptr && threadIdx.x == 0) atomicAdd(s.hist + __popc(run) + ((s.flags[g] & SW_THIN) ? 33 : 0), 1ull);
     const uint32_t *dw = decw + (size_t)g * N;
     uint32_t acc = 0;
     for (int i = c0 + threadIdx.x; i < cc; i += blockDim.x) {
@@ -629,13 +700,31 @@ sw2_syn_kernel(const uint32_t *__restrict__ decw, SwGroups s, const int32_t *__r
         else { n = n + 1; cont = true; }
     }
     const uint32_t next = __ballot_sync(0xffffffffu, cont);
+    const uint32_t thin = s.flags[g] & SW_THIN;
     if (next) {
         if (cont) s.n_pos[slot] = n;
-        if (f == 0) { s.run[g] = next; s.flags[g] = 0; }
+        // all running frames of a group started the position together, so they share n
+        const int n_run = __shfl_sync(0xffffffffu, n, __ffs(next) - 1);
+        if (f == 0) {
+            uint32_t fl = thin;
+            if (!thin && s.thin_pr != nullptr && __popc(next) <= kSwThinLanes && n_run >= 2 && max_iter - n_run >= kSwThinMinLeft) {
+                uint32_t map = 0;
+                for (int k = 0; k < kSwThinLanes; k++) {
+                    const int sl = sw_nth_set_bit(next, k);
+                    map |= (uint32_t)(sl < 0 ? 0xff : sl) << (8 * k);
+                }
+                const int e0 = __ldg(row_ptr + c0), e1 = __ldg(row_ptr + r[3]);
+                if (e1 - e0 <= s.thin_edges) {
+                    s.thin_map[g] = map; s.thin_e0[g] = e0; s.thin_ne[g] = e1 - e0;
+                    fl = SW_THIN | SW_THIN_IN;
+                }
+            }
+            s.run[g] = next; s.flags[g] = fl;
+        }
     } else {  // the group's slowest frame has left position t
         s.n_pos[slot] = 0;
         if (f == 0) {
-            if (t + 1 < L) { s.pos[g] = t + 1; s.run[g] = s.valid[g]; s.flags[g] = SW_INIT; }
+            if (t + 1 < L) { s.pos[g] = t + 1; s.run[g] = s.valid[g]; s.flags[g] = SW_INIT | (thin ? SW_THIN_OUT : 0u); }
             else { s.run[g] = 0; s.flags[g] = SW_FINAL; }
         }
     }

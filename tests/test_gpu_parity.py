@@ -412,15 +412,16 @@ def test_drain_tail_compaction(code18432, orc18432, cws):
 
 
 @pytest.mark.parametrize("switches", [{}, {"DNALDPC_SW_ZERO": "1", "DNALDPC_SW_CHUNK": "64", "DNALDPC_SW_PIECE": "32"},
-                                      {"DNALDPC_SW_LOCKSTEP": "1"}], ids=["groups", "groups-zero-chunk64-piece32", "lockstep"])
+                                      {"DNALDPC_SW_THIN": "0", "DNALDPC_SW_PACKED": "0"}, {"DNALDPC_SW_LOCKSTEP": "1"}],
+                         ids=["groups", "groups-zero-chunk64-piece32", "groups-no-straggler-mode", "lockstep"])
 def test_sliding_window_decoder(switches, monkeypatch):
     """sliding-window BP for SC-LDPC codes (dnaldpc_decode_window = Run_SW_Decoder, dec.cpp:2092-2196) on the
     generated (3,6) SC code: (a) the golden vectors produced by the unmodified reference, (b) a ragged batch (frames that
     leave a window position after 0..max_iter extra updates share warp groups; 100 frames through 2 groups of slots)
     against the oracle, for several window sizes incl. win == L (one window over the whole code). Variants: continuous
     batching by group (the default), the same with every group's message arrays cleared per refill, 64-frame staging
-    chunks and 32-frame copy pieces (groups wait for frames that are still on their way), and the wave-lock-step
-    schedule of the first version."""
+    chunks and 32-frame copy pieces (groups wait for frames that are still on their way), the same without the straggler
+    side arrays and lane packing, and the wave-lock-step schedule of the first version."""
     for k, v in switches.items():
         monkeypatch.setenv(k, v)
     g = np.load(os.path.join(ol.GOLDEN, "golden_sw.npz"))
