@@ -459,6 +459,31 @@ def test_sliding_window_decoder(switches, monkeypatch):
     dec.close()
 
 
+def test_sliding_window_generic_degrees():
+    """The window decoder on matrices that are not spatially coupled, with a window description laid over them: a
+    column-weight-10 random code (row degree 20: the generic check / bit update loops instead of the register kernels)
+    and the n=18432 code (row degree 72, column weight 8). Checks reach columns Init_SW_Decoder has not touched yet, so
+    the zeros alloc_entry leaves in the messages are operands (the per-refill clearing path). Against the oracle."""
+    import gen_regular_pchk
+    rs = np.random.RandomState(808)
+    row_ptr, col_idx = gen_regular_pchk.gen_regular(640, 320, 10, 3, no4cycle=False)
+    cases = [((320, 640, row_ptr, col_idx), None, 8, 2, 3, [80] * 8 + [0], [36] * 8 + [32], 70, 6),
+             (None, ol.PCHK_18432, 6, 2, 2, [3072] * 6 + [0], [340] * 6 + [8], 40, 4)]
+    for csr, path, L, w, win, Mv, Mc, F, mi in cases:
+        code = ldpc.Code(path) if path else ldpc.Code(csr=csr)
+        orc = ol.Oracle(path) if path else ol.Oracle(csr=csr)
+        Mv, Mc = np.array(Mv, np.int32), np.array(Mc, np.int32)
+        eps = rs.choice([0.0, 0.004, 0.01, 0.03], size=F)
+        lr = np.exp(np.where(rs.rand(F, code.N) < eps[:, None], -1.0, 1.0) * rs.uniform(2.0, 5.0, (F, code.N)))
+        dec = ldpc.Decoder(code, wave_frames=32)
+        r = dec.decode_window(lr, mi, L, w, win, Mv, Mc, want=("bits", "iters", "ok", "pchk"))
+        for f in range(F):
+            o = orc.decode_sw(lr[f], mi, L, w, win, Mv, Mc)
+            assert r["iters"][f] == o["n"] and r["ok"][f] == o["ok"], (code.N, f)
+            assert np.array_equal(r["bits"][f], o["dblk"]) and np.array_equal(r["pchk"][f].astype(np.int8), o["pchk"]), (code.N, f)
+        dec.close()
+
+
 def test_sliding_window_multi_device():
     """dnaldpc_decode_window with several devices: every device decodes a contiguous share of the frames; results equal
     the one-device decoder's (frames are independent, DNA_main.cpp:629-651)."""
