@@ -40,15 +40,16 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=200):
         self.gpu = gpu_index
+        self.period_ms = period_ms
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -157,6 +158,8 @@ def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
     st = torch.cuda.current_stream().cuda_stream
     W = (N + 31) // 32
     out = {}
+    sel = set(args.secondary.split(","))
+    want = lambda name: "all" in sel or name in sel  # noqa: E731
 
     def run_device(dc, kind, d_in, F, param, max_iter, n_, flags=0, b_iter=B_ITER, reps=1):
         d_bits = torch.empty((F, (n_ + 31) // 32), dtype=torch.int32, device=dev)
@@ -174,77 +177,84 @@ def secondary_regimes(ldpc, torch, dec, code, d_cw, args, peak):
                 "whole_step_gbs": b_iter * fi / (ms * 1e-3) / 1e9, "frac": b_iter * fi / (ms * 1e-3) / 1e9 / peak}
 
     # converging BSC frames (the pipeline's real regime), two batch sizes
-    for F in (65536, 1000000):
+    for F in (65536, 1000000) if want("bsc") else ():
         d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
         dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, 0.006, d_in.data_ptr(), st)
         out["bsc_eps0.006_%d" % F] = run_device(dec, ldpc.IN_BSC_BITS, d_in, F, 0.006, args.max_iter, N)
         del d_in
-    # configs[2]: vote counts, 1M frames
-    F = 1000000
-    d_in = torch.empty((F, N), dtype=torch.int8, device=dev)
-    dec.synth_vote_device(d_cw.data_ptr(), 272, args.seed, 0, F, 3.9, 0.01, d_in.data_ptr(), st)
-    out["c3_vote_i8_1000000"] = run_device(dec, ldpc.IN_VOTE_I8, d_in, F, 0.02, args.max_iter, N)
-    # the same frames through the host-buffer call (pinned memory, copies inside the timed region)
-    Fh = 131072
-    h_in = torch.empty((Fh, N), dtype=torch.int8).pin_memory(); h_in.copy_(d_in[:Fh])
-    same_size = run_device(dec, ldpc.IN_VOTE_I8, d_in[:Fh], Fh, 0.02, args.max_iter, N)  # the ratio compares batches of one size
-    del d_in
-    out["c3_vote_i8_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_VOTE_I8, h_in, Fh, 0.02, args.max_iter, same_size)
-    del h_in
-    # configs[3]: AWGN at Eb/N0 = 4.6 dB
-    F = 262144
-    sigma = ldpc.std_dev(4.6, 1 - M / N)
-    d_in = torch.empty((F, N), dtype=torch.float32, device=dev)
-    dec.synth_awgn_device(d_cw.data_ptr(), 272, args.seed, 0, F, sigma, d_in.data_ptr(), st)
-    out["c4_awgn_f32_%d" % F] = run_device(dec, ldpc.IN_AWGN_F32, d_in, F, sigma, args.max_iter, N)
-    Fh = 65536
-    h_in = torch.empty((Fh, N), dtype=torch.float32).pin_memory(); h_in.copy_(d_in[:Fh])
-    same_size = run_device(dec, ldpc.IN_AWGN_F32, d_in[:Fh], Fh, sigma, args.max_iter, N)
-    del d_in
-    out["c4_awgn_f32_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_AWGN_F32, h_in, Fh, sigma, args.max_iter, same_size)
-    del h_in
-    # LLR text-file style input: fp64 LLRs, exp on the host with libm (what the CLI does); bound by libm exp on the host cores
-    Fh = 16384
-    d_b = torch.empty((Fh, W), dtype=torch.int32, device=dev)
-    dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, Fh, 0.006, d_b.data_ptr(), st)
-    torch.cuda.synchronize()
-    bits = np.unpackbits(d_b.cpu().numpy().view(np.uint8).reshape(Fh, W * 4), axis=1, bitorder="little")[:, :N]
-    L = float(np.log((1 - 0.006) / 0.006))
-    h_llr = torch.from_numpy(np.where(bits == 0, L, -L)).pin_memory()
-    del d_b, bits
-    out["llr_f64_host_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None, flags=ldpc.FLAG_HOST_EXP)
-    out["llr_f64_device_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None)
-    del h_llr
-    # min-sum and fp32 at the headline operating point (no frame converges: pure kernel throughput)
-    F = 16384
-    d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
-    dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, args.eps, d_in.data_ptr(), st)
-    out["minsum_eps%g_%d" % (args.eps, F)] = run_device(dec, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, flags=ldpc.FLAG_MINSUM)
-    d32 = ldpc.Decoder(code, devices=[torch.cuda.current_device()], wave_frames=args.wave, precision=ldpc.PREC_F32)
-    out["fp32_eps%g_%d" % (args.eps, F)] = run_device(d32, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, b_iter=0.5 * B_ITER)
-    d32.close()
-    del d_in
-    # configs[4]: Neal-style random regular code n=65536, column weight 3, rate 0.9
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import gen_regular_pchk
-    n5, m5 = 65536, 6554
-    row_ptr, col_idx = gen_regular_pchk.gen_regular(n5, m5, 3, 5)
-    code5 = ldpc.Code(csr=(m5, n5, row_ptr, col_idx))
-    dec5 = ldpc.Decoder(code5, devices=[torch.cuda.current_device()], wave_frames=args.wave)
-    b5 = 32 * code5.E + 8.25 * n5
-    for eps5, F5 in ((0.02, 8192), (0.004, 32768)):
-        d_in = torch.empty((F5, n5 // 32), dtype=torch.int32, device=dev)
-        dec5.synth_bsc_device(None, 0, args.seed, 0, F5, eps5, d_in.data_ptr(), st)  # all-zero codeword
-        out["c5_n65536_eps%g_%d" % (eps5, F5)] = run_device(dec5, ldpc.IN_BSC_BITS, d_in, F5, eps5, 50, n5, b_iter=b5)
+    if want("vote"):
+        # configs[2]: vote counts, 1M frames
+        F = 1000000
+        d_in = torch.empty((F, N), dtype=torch.int8, device=dev)
+        dec.synth_vote_device(d_cw.data_ptr(), 272, args.seed, 0, F, 3.9, 0.01, d_in.data_ptr(), st)
+        out["c3_vote_i8_1000000"] = run_device(dec, ldpc.IN_VOTE_I8, d_in, F, 0.02, args.max_iter, N)
+        # the same frames through the host-buffer call (pinned memory, copies inside the timed region)
+        Fh = 131072
+        h_in = torch.empty((Fh, N), dtype=torch.int8).pin_memory(); h_in.copy_(d_in[:Fh])
+        same_size = run_device(dec, ldpc.IN_VOTE_I8, d_in[:Fh], Fh, 0.02, args.max_iter, N)  # the ratio compares batches of one size
         del d_in
-    dec5.close()
-    out["sw_z1024_l24_eps0.03_8192"] = sliding_window_leg(ldpc, torch, args)
+        out["c3_vote_i8_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_VOTE_I8, h_in, Fh, 0.02, args.max_iter, same_size)
+        del h_in
+    if want("awgn"):
+        # configs[3]: AWGN at Eb/N0 = 4.6 dB
+        F = 262144
+        sigma = ldpc.std_dev(4.6, 1 - M / N)
+        d_in = torch.empty((F, N), dtype=torch.float32, device=dev)
+        dec.synth_awgn_device(d_cw.data_ptr(), 272, args.seed, 0, F, sigma, d_in.data_ptr(), st)
+        out["c4_awgn_f32_%d" % F] = run_device(dec, ldpc.IN_AWGN_F32, d_in, F, sigma, args.max_iter, N)
+        Fh = 65536
+        h_in = torch.empty((Fh, N), dtype=torch.float32).pin_memory(); h_in.copy_(d_in[:Fh])
+        same_size = run_device(dec, ldpc.IN_AWGN_F32, d_in[:Fh], Fh, sigma, args.max_iter, N)
+        del d_in
+        out["c4_awgn_f32_host_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_AWGN_F32, h_in, Fh, sigma, args.max_iter, same_size)
+        del h_in
+    if want("llr"):
+        # LLR text-file style input: fp64 LLRs, exp on the host with libm (what the CLI does); bound by libm exp on the host cores
+        Fh = 16384
+        d_b = torch.empty((Fh, W), dtype=torch.int32, device=dev)
+        dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, Fh, 0.006, d_b.data_ptr(), st)
+        torch.cuda.synchronize()
+        bits = np.unpackbits(d_b.cpu().numpy().view(np.uint8).reshape(Fh, W * 4), axis=1, bitorder="little")[:, :N]
+        L = float(np.log((1 - 0.006) / 0.006))
+        h_llr = torch.from_numpy(np.where(bits == 0, L, -L)).pin_memory()
+        del d_b, bits
+        out["llr_f64_host_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None, flags=ldpc.FLAG_HOST_EXP)
+        out["llr_f64_device_exp_%d" % Fh] = host_leg(ldpc, torch, dec, ldpc.IN_LLR_F64, h_llr, Fh, 0.0, args.max_iter, None)
+        del h_llr
+    if want("minsum_fp32"):
+        # min-sum and fp32 at the headline operating point (no frame converges: pure kernel throughput)
+        F = 16384
+        d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+        dec.synth_bsc_device(d_cw.data_ptr(), 272, args.seed, 0, F, args.eps, d_in.data_ptr(), st)
+        out["minsum_eps%g_%d" % (args.eps, F)] = run_device(dec, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, flags=ldpc.FLAG_MINSUM)
+        d32 = ldpc.Decoder(code, devices=[torch.cuda.current_device()], wave_frames=args.wave, precision=ldpc.PREC_F32)
+        out["fp32_eps%g_%d" % (args.eps, F)] = run_device(d32, ldpc.IN_BSC_BITS, d_in, F, args.eps, args.max_iter, N, b_iter=0.5 * B_ITER)
+        d32.close()
+        del d_in
+    if want("c5"):
+        # configs[4]: Neal-style random regular code n=65536, column weight 3, rate 0.9
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gen_regular_pchk
+        n5, m5 = 65536, 6554
+        row_ptr, col_idx = gen_regular_pchk.gen_regular(n5, m5, 3, 5)
+        code5 = ldpc.Code(csr=(m5, n5, row_ptr, col_idx))
+        dec5 = ldpc.Decoder(code5, devices=[torch.cuda.current_device()], wave_frames=args.wave)
+        b5 = 32 * code5.E + 8.25 * n5
+        for eps5, F5 in ((0.02, 8192), (0.004, 32768)):
+            d_in = torch.empty((F5, n5 // 32), dtype=torch.int32, device=dev)
+            dec5.synth_bsc_device(None, 0, args.seed, 0, F5, eps5, d_in.data_ptr(), st)  # all-zero codeword
+            out["c5_n65536_eps%g_%d" % (eps5, F5)] = run_device(dec5, ldpc.IN_BSC_BITS, d_in, F5, eps5, 50, n5, b_iter=b5)
+            del d_in
+        dec5.close()
+    if want("sw"):
+        out["sw_z1024_l24_eps0.03_8192"] = sliding_window_leg(ldpc, torch, args)
     return out
 
 
 def sliding_window_leg(ldpc, torch, args, Z=1024, Lc=24, win=6, F=8192, eps=0.03, max_iter=20):
     """dnaldpc_decode_window (Run_SW_Decoder, dec.cpp:2092-2196) on a terminated (3,6) SC-LDPC code from tools/gen_sc_pchk.py:
     all-zero codeword through a BSC, fp64 ratios in pinned host memory, host buffers out; the C-ABI call alone is timed."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_sc_pchk
     Cc = ldpc.C
     Ms, Ns, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(Z, Lc, 11)
@@ -271,16 +281,23 @@ def sliding_window_leg(ldpc, torch, args, Z=1024, Lc=24, win=6, F=8192, eps=0.03
             raise RuntimeError(ldpc.lib().dnaldpc_last_error())
     go(min(F, args.wave))
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    go(F)
-    dt = time.perf_counter() - t0
+    sampler = ClockSampler(torch.cuda.current_device(), period_ms=50)
+    sampler.start()
+    dts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        go(F)
+        dts.append(time.perf_counter() - t0)
+    dt = min(dts)
+    clocks = sampler.stop()
     stt = dec.stats()
     ok = h_ok.numpy()
     good = torch.from_numpy(ok.astype(bool))
     r = {"frames": F, "ms": dt * 1e3, "gbit_s": F * Ns / dt / 1e9, "frames_per_s": F / dt, "fer": 1.0 - float(ok.mean()),
          "code": {"Z": Z, "L": Lc, "N": Ns, "M": Ms, "window": win}, "max_extra_updates": max_iter, "ticks": stt["waves"],
-         "kernel_launches": stt["kernel_launches"], "h2d_bytes": F * Ns * 8, "d2h_bytes": F * (Ws * 4 + 5),
-         "flagged_frames_are_the_sent_codeword": bool((h_bits[good] == 0).all().item()) if ok.any() else True}
+         "kernel_launches": stt["kernel_launches"], "ms_runs": [x * 1e3 for x in dts], "clocks": clocks, "h2d_bytes": F * Ns * 8, "d2h_bytes": F * (Ws * 4 + 5),
+         "flagged_frames": int(ok.sum()), "flagged_frames_with_bit_errors": int((h_bits[good] != 0).any(dim=1).sum().item()) if ok.any() else 0,
+         "bit_errors_all_frames": int(np.unpackbits(h_bits.numpy().view(np.uint8)).sum())}
     dec.close()
     return r
 
@@ -589,6 +606,7 @@ def main():
     ap.add_argument("--ref-frames-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary regimes (converging frames, configs 3-5, fp32, min-sum, host-buffer kinds)")
+    ap.add_argument("--secondary", default="all", help="comma-separated subset of the secondary regimes: bsc,vote,awgn,llr,minsum_fp32,c5,sw (default all)")
     ap.add_argument("--inproc-frames", type=int, default=1000000, help="N > 1: frames of the one batch rank 0 decodes through the library's own multi-GPU dispatch")
     ap.add_argument("--alg", default="bp", choices=["bp", "minsum"], help="bp = sum-product (the metric); minsum = floating min-sum (SURVEY 8f-4)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f64 = bit-exact mode (the metric); f32 = optional fast mode")
