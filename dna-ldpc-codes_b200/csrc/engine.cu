@@ -720,14 +720,14 @@ int Engine::sw_groups(const Code &code, const dnaldpc_window &w, const std::vect
     // straggler mode (sw2_thin_copy_kernel): side arrays with 4 slots per edge for the edges of one window's checks
     int thin_edges = 0;
     for (int t = 0; t < L; t++) thin_edges = std::max(thin_edges, code.row_ptr[sched[(size_t)8 * t + 3]] - code.row_ptr[sched[(size_t)8 * t + 2]]);
-    const bool thin_on = !(getenv("DNALDPC_SW_THIN") && atoi(getenv("DNALDPC_SW_THIN")) == 0) && thin_edges > 0;  // A/B switch
+    bool thin_on = !(getenv("DNALDPC_SW_THIN") && atoi(getenv("DNALDPC_SW_THIN")) == 0) && thin_edges > 0;  // A/B switch
     if (thin_on) {
         const size_t need = (size_t)G * thin_edges * kSwThinLanes * 2 * sizeof(double);
         if (need > sw_cap_thin_) {
             if (d_sw_thin_) cudaFree(d_sw_thin_);
             d_sw_thin_ = nullptr; sw_cap_thin_ = 0;
-            CK(cudaMalloc(&d_sw_thin_, need));
-            sw_cap_thin_ = need;
+            if (cudaMalloc(&d_sw_thin_, need) == cudaSuccess) sw_cap_thin_ = need;
+            else { cudaGetLastError(); d_sw_thin_ = nullptr; thin_on = false; }  // short of memory: decode without the side arrays
         }
     }
     // A chunk is copied in pieces of about 64 MB; behind every piece the copy stream publishes how many frames of the
