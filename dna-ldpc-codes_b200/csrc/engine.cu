@@ -612,7 +612,23 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
     cudaStream_t st = own_stream_;
     stats = dnaldpc_stats{};
     stats.frames = F;
-    const int G = (int)std::min<int64_t>((F + 31) / 32, wave_frames_ / 32);
+    const bool lockstep = getenv("DNALDPC_SW_LOCKSTEP") && atoi(getenv("DNALDPC_SW_LOCKSTEP")) != 0;  // A/B switch, see below
+    // Slots of the window decoder. Most of a tick's launches are short (a few frames per group iterate on), so more
+    // groups in flight fill the machine better (16 384 frames on the Z=1024 x L=24 code: 4096 slots 28.1 k frames/s, 8192
+    // 30.6 k, 16 384 31.7 k): up to 4 x wave_frames when that takes at most a third of the free device memory. Decided
+    // once per engine; DNALDPC_SW_SLOTS_X = 1 / 2 / 4 overrides.
+    if (sw_slots_ == 0) {
+        sw_slots_ = wave_frames_;
+        if (!lockstep) {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t per_slot = ((size_t)2 * E_ + N_) * sizeof(double) + (size_t)N_ / 8 + 64;
+            const int want_x = getenv("DNALDPC_SW_SLOTS_X") ? atoi(getenv("DNALDPC_SW_SLOTS_X")) : 0;
+            for (int x : {4, 2})
+                if (want_x ? x == want_x : (size_t)wave_frames_ * x * per_slot <= free_b / 3) { sw_slots_ = wave_frames_ * x; break; }
+        }
+    }
+    const int G = (int)std::min<int64_t>((F + 31) / 32, (lockstep ? wave_frames_ : sw_slots_) / 32);
     int rc = ensure_slots(G, false);
     if (rc) return rc;
     if (G > sw_cap_groups_) {
@@ -639,7 +655,7 @@ int Engine::decode_window_host(const Code &code, const dnaldpc_window &w, const 
     }
     // A/B switch: the wave-lock-step schedule of the first version (every position runs until the slowest frame of the
     // wave has left it) instead of continuous batching by group
-    if (getenv("DNALDPC_SW_LOCKSTEP") && atoi(getenv("DNALDPC_SW_LOCKSTEP")) != 0) return sw_lockstep(w, sched, lratio, F, max_iter, out, G);
+    if (lockstep) return sw_lockstep(w, sched, lratio, F, max_iter, out, G);
     return sw_groups(code, w, sched, lratio, F, max_iter, out, G);
 }
 

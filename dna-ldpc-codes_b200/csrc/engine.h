@@ -113,6 +113,7 @@ class Engine {
     int32_t *d_slot_ = nullptr;                          // 4 ints per slot (frame, iter, harv_frame, harv_iter)
     void *d_sw_lr_ = nullptr;                            // sliding-window mode: second message array (check -> bit)
     int sw_cap_groups_ = 0;
+    int sw_slots_ = 0;                                   // sliding-window mode: slots in flight (decided at the first call)
     int32_t *d_edge_row_ = nullptr;                      // sliding-window mode: check of every edge
     int32_t *d_col_row_ = nullptr;                       // sliding-window mode: check of the k-th entry of a column
     int32_t *d_sw_sched_ = nullptr;                      // sliding-window mode: window ranges per position [L][8]
