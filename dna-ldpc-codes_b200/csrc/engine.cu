@@ -84,6 +84,8 @@ Engine::~Engine() {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_bounce_) cudaFreeHost(h_bounce_);
+    if (h_rows_) cudaFreeHost(h_rows_);
+    if (h_avail_) cudaFreeHost(h_avail_);
     if (ready_ev_) cudaEventDestroy(ready_ev_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : prof_ev_) if (e) cudaEventDestroy(e);
@@ -326,8 +328,17 @@ int Engine::launch_harvest_setup(const dnaldpc_input &in, const dnaldpc_output &
 int Engine::ensure_rows(int64_t frames) {
     if (frames > cap_rows_) {
         if (d_rows_) cudaFree(d_rows_);
-        d_rows_ = nullptr; cap_rows_ = 0;
+        if (h_rows_) cudaFreeHost(h_rows_);
+        if (h_avail_) cudaFreeHost(h_avail_);
+        d_rows_ = nullptr; h_rows_ = nullptr; h_avail_ = nullptr; cap_rows_ = 0;
         CK(cudaMalloc((void **)&d_rows_, (size_t)frames * 2 * sizeof(int32_t)));
+        // pinned mirrors for publishing through the copy engine (publish(..., dma)); without them the kernel is used
+        if (cudaMallocHost((void **)&h_rows_, (size_t)frames * 2 * sizeof(int32_t)) != cudaSuccess ||
+            cudaMallocHost((void **)&h_avail_, ((size_t)frames + 1) * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            if (h_rows_) cudaFreeHost(h_rows_);
+            h_rows_ = nullptr; h_avail_ = nullptr;
+        }
         cap_rows_ = frames;
     }
     return DNALDPC_OK;
@@ -339,10 +350,25 @@ int Engine::set_device() {
 }
 
 // Called from a source's producer thread while the tick thread is inside run(): touches neither err_ nor stats.
-int Engine::publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream) {
+int Engine::publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream, bool dma) {
     if (n <= 0) return DNALDPC_OK;
     const int64_t q0 = published_.load(std::memory_order_relaxed);
     if (q0 + n > cap_rows_) return DNALDPC_ERR_ARG;  // more frames published than the session announced
+    if (dma && !list_in && h_rows_) {
+        // From a copy stream: the table entries and the counter travel through the copy engine like the inputs before
+        // them. A kernel here would wait for a free SM slot - the persistent check pass holds every SM's registers for
+        // 1.5 ms at a time - and, the stream being in order, hold back the next piece's copy: wide inputs (fp64 ratios,
+        // 147 KB per frame, 33 MB pieces) then reached the engine at 14.5 GB/s with the link idle most of the time.
+        int32_t *hi = h_rows_ + q0, *ho = h_rows_ + cap_rows_ + q0;
+        for (int i = 0; i < n; i++) { hi[i] = row0_in + i; ho[i] = row0_out + i; }
+        h_avail_[q0 + n] = (unsigned long long)(q0 + n);  // one word per end position: never rewritten while a copy of it is pending
+        if (cudaMemcpyAsync(d_rows_ + q0, hi, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_rows_ + cap_rows_ + q0, ho, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_next_ + 1, h_avail_ + q0 + n, sizeof(unsigned long long), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            return DNALDPC_ERR_CUDA;
+        published_.store(q0 + n, std::memory_order_release);
+        return DNALDPC_OK;
+    }
     publish_kernel<<<1, 1024, 0, stream>>>(d_rows_, d_rows_ + cap_rows_, (long long)q0, n, list_in, row0_in, row0_out, d_next_ + 1);
     if (cudaGetLastError() != cudaSuccess) return DNALDPC_ERR_CUDA;
     published_.store(q0 + n, std::memory_order_release);

@@ -53,7 +53,8 @@ class Engine {
     // Appends n frames to the queue: input rows list_in[0..n) (a DEVICE array) or row0_in.. when list_in == NULL,
     // output rows row0_out... Ordered on `stream` (the stream that made the frames' inputs resident). One producer at
     // a time.
-    int publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream);
+    // dma: write the queue entries with copy-engine transfers instead of a kernel (for producers on a copy stream).
+    int publish(const int32_t *list_in, int row0_in, int row0_out, int n, cudaStream_t stream, bool dma = false);
     // list_out[0..*count) = prev_list[k] (k itself when prev_list == NULL) for every k < n with ok[k] == 0, in ascending
     // k (the frames a re-decoding round takes, decoder.py:641-660). DEVICE arrays; *count_dev is a device int.
     int failed_rows(const uint8_t *ok, const int32_t *prev_list, int n, int32_t *list_out, int32_t *count_dev, cudaStream_t stream);
@@ -135,6 +136,8 @@ class Engine {
     unsigned long long *d_next_ = nullptr;               // {next_frame, avail, iter_sum}
     int32_t *d_rows_ = nullptr;                          // frame queue: in_row[cap_rows_], out_row[cap_rows_]
     int64_t cap_rows_ = 0;
+    int32_t *h_rows_ = nullptr;                          // pinned mirror of d_rows_ (publish through the copy engine)
+    unsigned long long *h_avail_ = nullptr;              // pinned: value of `avail` after the piece that ends at position q
     std::atomic<int64_t> published_{0};                  // frames handed to publish() in this session (host view)
     uint64_t *d_synth_thr_ = nullptr;                    // Poisson thresholds of the vote-count generator
     int32_t *d_iters_ = nullptr;                         // per-frame scratch when the caller does not want them

@@ -229,7 +229,8 @@ class HostSource : public FrameSource {
             } else {
                 if (!cuda_ok(cudaMemcpy2DAsync(dst, b_.packed, src, b_.stride, b_.packed, (size_t)n, cudaMemcpyHostToDevice, st), "cudaMemcpy2DAsync(H2D)")) return;
             }
-            const int rc = e_.publish(nullptr, (int)(q % in_ring_), (int)(q % out_ring_), n, st);
+            static const bool dma_publish = !(getenv("DNALDPC_PUBLISH_KERNEL") && atoi(getenv("DNALDPC_PUBLISH_KERNEL")) != 0);  // A/B switch
+            const int rc = e_.publish(nullptr, (int)(q % in_ring_), (int)(q % out_ring_), n, st, dma_publish);
             if (rc) { set_fail(rc, rc == DNALDPC_ERR_CUDA ? "CUDA error while publishing frames to the engine's queue" : "frame queue overflow"); return; }
             launches_++;
             {
