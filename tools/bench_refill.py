@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--wave", type=int, default=4096)
     ap.add_argument("--c5", action="store_true", help="also the n=65536 column-weight-3 code at eps 0.004")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--kind", default="bsc", choices=["bsc", "vote", "awgn"], help="input kind of the n=18432 probes (vote: configs[2], awgn: configs[3] at 4.6 dB)")
     a = ap.parse_args()
     import torch
     import _pkg
@@ -33,16 +34,27 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     res = {"tag": a.tag, "env": {k: v for k, v in os.environ.items() if k.startswith("DNALDPC_")}}
 
-    def probe(dec, n, b_iter, F, eps, d_cw, n_cw):
+    def probe(dec, n, b_iter, F, eps, d_cw, n_cw, kind="bsc"):
         W = (n + 31) // 32
-        d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
-        dec.synth_bsc_device(d_cw.data_ptr() if d_cw is not None else None, n_cw, 7, 0, F, eps, d_in.data_ptr(), st)
+        if kind == "vote":
+            d_in = torch.empty((F, n), dtype=torch.int8, device=dev)
+            dec.synth_vote_device(d_cw.data_ptr(), n_cw, 7, 0, F, 3.9, 0.01, d_in.data_ptr(), st)
+            k_in, param = ldpc.IN_VOTE_I8, 0.02
+        elif kind == "awgn":
+            param = ldpc.std_dev(4.6, 1 - 2048 / 18432)
+            d_in = torch.empty((F, n), dtype=torch.float32, device=dev)
+            dec.synth_awgn_device(d_cw.data_ptr(), n_cw, 7, 0, F, param, d_in.data_ptr(), st)
+            k_in = ldpc.IN_AWGN_F32
+        else:
+            d_in = torch.empty((F, W), dtype=torch.int32, device=dev)
+            dec.synth_bsc_device(d_cw.data_ptr() if d_cw is not None else None, n_cw, 7, 0, F, eps, d_in.data_ptr(), st)
+            k_in, param = ldpc.IN_BSC_BITS, eps
         d_bits = torch.empty((F, W), dtype=torch.int32, device=dev)
         d_it = torch.empty(F, dtype=torch.int32, device=dev)
         d_ok = torch.empty(F, dtype=torch.uint8, device=dev)
 
         def go():
-            dec.decode_device(ldpc.IN_BSC_BITS, d_in.data_ptr(), F, a.max_iter, param=eps, bits_ptr=d_bits.data_ptr(),
+            dec.decode_device(k_in, d_in.data_ptr(), F, a.max_iter, param=param, bits_ptr=d_bits.data_ptr(),
                               iters_ptr=d_it.data_ptr(), ok_ptr=d_ok.data_ptr(), stream=st)
         go()
         dec.set_profiling(2)
@@ -62,7 +74,7 @@ def main():
     cw = np.fromfile(bench.CW_BITS, dtype=np.uint8).view(np.int32).reshape(272, -1)
     d_cw = torch.from_numpy(cw).to(dev)
     for F in a.frames:
-        res["n18432_%d" % F] = probe(dec, bench.N, bench.B_ITER, F, a.eps, d_cw, 272)
+        res["n18432_%s_%d" % (a.kind, F)] = probe(dec, bench.N, bench.B_ITER, F, a.eps, d_cw, 272, a.kind)
     dec.close()
     if a.c5:
         import gen_regular_pchk
