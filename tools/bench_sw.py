@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=20)
     ap.add_argument("--wave", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--warm", type=int, default=0, help="frames of the warm-up call (default: one wave)")
+    ap.add_argument("--warm", type=int, default=0, help="frames of the warm-up call (default: one wave; negative: no warm-up call, e.g. under ncu)")
     a = ap.parse_args()
     ldpc = _pkg.load()
     M, N, row_ptr, col_idx, Mv, Mc = gen_sc_pchk.gen_sc(a.z, a.L, 11)
@@ -56,7 +56,8 @@ def main():
         rc = ldpc.lib().dnaldpc_decode_window(dec._h, C.byref(wd), lr.data_ptr(), nf, a.max_iter, C.byref(out))
         if rc:
             raise RuntimeError(ldpc.lib().dnaldpc_last_error())
-    call(min(a.frames, a.warm or a.wave))  # warm-up: slot arrays, staging buffers
+    if a.warm >= 0:
+        call(min(a.frames, a.warm or a.wave))  # warm-up: slot arrays, staging buffers
     dts = []
     for _ in range(a.reps):
         t0 = time.perf_counter()
