@@ -9,9 +9,12 @@
 //   * a bit that has left the window keeps its bit->check message while the checks it still touches keep running, so
 //     e->pr and e->lr are both live: TWO message arrays pr[G][E][32], lr[G][E][32], both zero at the start
 //     (alloc_entry, mod2sparse.cpp:61-62);
-//   * the frames of a wave walk through the window positions together: a frame that satisfies the bounded syndrome of
-//     position t early waits (its messages untouched) until the slowest frame of the wave has finished t. Frames are
-//     independent, so each frame's arithmetic - and hence its result - is exactly the reference's;
+//   * a frame that satisfies the bounded syndrome of position t early waits (its messages untouched) for the other
+//     frames it shares warps with. Frames are independent, so each frame's arithmetic - and hence its result - is
+//     exactly the reference's. Two schedules: the sw_* kernels (first half of the file) walk a whole wave through
+//     the positions together (Engine::sw_lockstep, A/B switch DNALDPC_SW_LOCKSTEP=1); the sw2_* kernels (second half,
+//     the default, Engine::sw_groups) give every group of 32 frames its own position, refill a group as soon as it is
+//     through, pack the lanes of groups in which few frames still iterate and move 1-4 stragglers into side arrays;
 //   * checks of degree <= 8 (the (3,6) protograph codes) run through sw_row_reg_kernel: the row's messages in registers,
 //     all loads in flight at once, the in-range division sequences of bp_math.cuh (bit-identical to IEEE division on
 //     their ranges; anything else falls back, per lane, to the full-range loop); higher degrees use the generic
